@@ -1,0 +1,691 @@
+// api.cu — the C ABI of include/svgpu.h: context, parameter normalisation, scratch management and
+// host<->device staging around the kernels in sgbm.cu / bm.cu / image_ops.cu.
+// There is deliberately no CPU path in this file: every entry point either runs CUDA kernels on the
+// context's device or fails with an SV_* code.
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace svgpu;
+
+struct svgpu_ctx {
+  int device = 0, W = 0, H = 0;
+  cudaStream_t own = nullptr, st = nullptr;
+  std::mutex mu;
+  std::string err;
+
+  int16_t* map1[2] = {nullptr, nullptr};
+  uint16_t* map2[2] = {nullptr, nullptr};
+  double* Qdev = nullptr;
+  bool haveQ = false, haveDepth = false, haveSgbm = false, haveBm = false;
+  float baseline = 0, focal = 0;
+  SgbmCfg cfg{};
+  BmCfg bm{};
+  int variant = -1;  // aggregation schedule; -1 = default
+
+  int maxBatch = 1;
+  // scratch for the SGBM core, sized for (cfg, allocBatch)
+  SgbmScratch sc{};
+  int allocBatch = 0;
+  size_t allocCells = 0;
+  int allocWp = 0;
+  // device staging of caller images for SV_MEM_HOST calls and intermediates of the fused chain
+  std::vector<void*> pool;  // everything cudaMalloc'ed lazily through dev_buf()
+  struct Buf { void* p = nullptr; size_t n = 0; };
+  Buf stLeft, stRight, stDisp, stXyz, stDepth, stRectL, stRectR, stGrayL, stGrayR, stTmpH, stTmpG, stDisp2, stLabels,
+      stSizes, stSrc, stBmL, stBmR;
+  int* minScratch = nullptr;
+
+  LaunchStats stats;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stageMs[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(svgpu_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(svgpu_ctx* c, cudaError_t e, const char* where) {
+  const int code = (e == cudaErrorMemoryAllocation) ? SV_OOM : SV_CUDA_ERROR;
+  return fail(c, code, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((c), e__, #call); } while (0)
+
+int ensure(svgpu_ctx* c, svgpu_ctx::Buf& b, size_t bytes) {
+  if (b.n >= bytes && b.p) return SV_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.n = 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(staging)");
+  b.n = bytes;
+  return SV_OK;
+}
+void release(svgpu_ctx::Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.n = 0; }
+
+void free_scratch(svgpu_ctx* c) {
+  cudaFree(c->sc.planesL); cudaFree(c->sc.planesR); cudaFree(c->sc.C); cudaFree(c->sc.S); cudaFree(c->sc.wtaKey);
+  cudaFree(c->sc.dispRaw); cudaFree(c->sc.status); cudaFree(c->sc.flags); cudaFree(c->sc.edges);
+  c->sc = SgbmScratch{};
+  c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0;
+}
+
+int ensure_scratch(svgpu_ctx* c, int batch) {
+  const SgbmCfg& g = c->cfg;
+  const size_t cells = g.W1 > 0 ? (size_t)g.W1 * g.H * g.D : 0;
+  if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->sc.dispRaw) return SV_OK;
+  free_scratch(c);
+  const size_t planeBytes = (size_t)batch * g.H * 6 * g.Wp;
+  const size_t w1 = g.W1 > 0 ? g.W1 : 0;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 256)); };
+  A((void**)&c->sc.planesL, planeBytes);
+  A((void**)&c->sc.planesR, planeBytes);
+  A((void**)&c->sc.C, (size_t)batch * cells * 2);
+  A((void**)&c->sc.S, (size_t)batch * cells * 2);
+  A((void**)&c->sc.wtaKey, (size_t)batch * g.H * w1 * 4);
+  A((void**)&c->sc.dispRaw, (size_t)batch * g.H * g.W * 2);
+  A((void**)&c->sc.status, 256);
+  A((void**)&c->sc.flags, sgbm_flags_bytes(g, batch));
+  A((void**)&c->sc.edges, sgbm_edges_bytes(g, batch));
+  if (e != cudaSuccess) { free_scratch(c); return cuda_fail(c, e, "cudaMalloc(sgbm scratch)"); }
+  cudaMemsetAsync(c->sc.status, 0, 256, c->st);
+  cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(g, batch), c->st);
+  c->sc.frameCells = cells;
+  c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp;
+  return SV_OK;
+}
+
+// A.1 parameter normalisation + the contract checks of this implementation
+int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
+  if (p.numDisparities <= 0 || p.numDisparities % 16 != 0) return fail(c, SV_INVALID_SETTINGS, "numDisparities must be a positive multiple of 16");
+  if (p.numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported");
+  if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4) return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH or MODE_HH4");
+  if (p.blockSize > 11 || (p.blockSize > 0 && p.blockSize % 2 == 0)) return fail(c, SV_INVALID_SETTINGS, "blockSize must be odd and <= 11");
+  if (p.preFilterCap > 63) return fail(c, SV_INVALID_SETTINGS, "preFilterCap must be <= 63");
+  g.W = c->W; g.H = c->H;
+  g.D = p.numDisparities; g.minD = p.minDisparity;
+  const int maxD = g.minD + g.D;
+  g.minX1 = std::max(maxD, 0);
+  g.W1 = (g.W + std::min(g.minD, 0)) - g.minX1;
+  g.P1 = p.P1 > 0 ? p.P1 : 2;
+  g.P2 = std::max(p.P2 > 0 ? p.P2 : 5, g.P1 + 1);
+  g.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+  g.d12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+  g.ftzero = std::max(p.preFilterCap, 15) | 1;
+  const int bs = p.blockSize > 0 ? p.blockSize : 5;
+  g.r = bs / 2;
+  g.mode = p.mode;
+  g.invalid = (g.minD - 1) * 16;
+  g.Wp = (g.W + 15) & ~15;
+  g.speckleWindowSize = p.speckleWindowSize;
+  g.speckleRange = p.speckleRange;
+  if (g.uniq > 100) return fail(c, SV_INVALID_SETTINGS, "uniquenessRatio must be <= 100");
+  // 16-bit headroom: every path cost L <= Ctrue + P2 must stay below MAX_COST, as in OpenCV's own contract
+  const long long maxC = (long long)bs * bs * (2 * g.ftzero + 63);
+  if (maxC + g.P2 > 32767) return fail(c, SV_INVALID_SETTINGS, "blockSize^2*(2*ftzero+63) + P2 exceeds the 16-bit cost range");
+  if (std::abs(g.minD) > 4096) return fail(c, SV_INVALID_SETTINGS, "minDisparity out of range");
+  return SV_OK;
+}
+
+struct HostIO {  // moves caller images through device staging for SV_MEM_HOST
+  svgpu_ctx* c;
+};
+
+int h2d_2d(svgpu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, int rows) {
+  CU(c, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyHostToDevice, c->st));
+  return SV_OK;
+}
+int d2h_2d(svgpu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitch, size_t widthBytes, int rows) {
+  CU(c, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyDeviceToHost, c->st));
+  return SV_OK;
+}
+
+int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const uint8_t* dr, size_t rs, size_t rf,
+             int16_t* dd, size_t ds, size_t df) {
+  int rc = ensure_scratch(c, std::max(n, c->maxBatch));
+  if (rc) return rc;
+  cudaError_t e = sgbm_forward(c->cfg, c->sc, n, dl, ls, lf, dr, rs, rf, dd, ds, df, c->st, &c->stats,
+                               c->timing ? c->ev : nullptr, c->variant);
+  if (e != cudaSuccess) return cuda_fail(c, e, "sgbm_forward");
+  if (c->cfg.speckleWindowSize > 0) {  // built-in stage of StereoSGBM::compute (A.7): newVal = INVALID, maxDiff = 16*range
+    rc = ensure(c, c->stLabels, (size_t)c->W * c->H * 4);
+    if (!rc) rc = ensure(c, c->stSizes, (size_t)c->W * c->H * 4);
+    if (rc) return rc;
+    for (int f = 0; f < n; f++) {
+      int nl = 0;
+      e = launch_filter_speckles((int16_t*)((uint8_t*)dd + f * df), ds, c->W, c->H, c->cfg.invalid, c->cfg.speckleWindowSize,
+                                 16 * c->cfg.speckleRange, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl);
+      c->stats.launches += nl;
+      if (e != cudaSuccess) return cuda_fail(c, e, "filter_speckles");
+    }
+  }
+  return SV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+SVGPU_API const char* svgpu_version(void) { return "svgpu 0.1 sm_100a"; }
+
+SVGPU_API int svgpu_create(int device, int width, int height, svgpu_ctx** out) {
+  if (!out) return SV_INVALID_SETTINGS;
+  *out = nullptr;
+  if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return SV_INVALID_SETTINGS;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SV_CUDA_ERROR;
+  if (cudaSetDevice(device) != cudaSuccess) return SV_CUDA_ERROR;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SV_CUDA_ERROR;
+  if (prop.major < 10) return SV_CUDA_ERROR;  // sm_100a SASS only, no fallback
+  svgpu_ctx* c = new (std::nothrow) svgpu_ctx();
+  if (!c) return SV_OOM;
+  c->device = device; c->W = width; c->H = height;
+  if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SV_CUDA_ERROR; }
+  c->st = c->own;
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  if (cudaMalloc((void**)&c->Qdev, 16 * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&c->minScratch, 256) != cudaSuccess) {
+    svgpu_destroy(c);
+    return SV_OOM;
+  }
+  *out = c;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_destroy(svgpu_ctx* c) {
+  if (!c) return SV_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  free_scratch(c);
+  for (int s = 0; s < 2; s++) { cudaFree(c->map1[s]); cudaFree(c->map2[s]); }
+  cudaFree(c->Qdev); cudaFree(c->minScratch);
+  for (svgpu_ctx::Buf* b : {&c->stLeft, &c->stRight, &c->stDisp, &c->stXyz, &c->stDepth, &c->stRectL, &c->stRectR, &c->stGrayL,
+                            &c->stGrayR, &c->stTmpH, &c->stTmpG, &c->stDisp2, &c->stLabels, &c->stSizes, &c->stSrc, &c->stBmL, &c->stBmR})
+    release(*b);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->own) cudaStreamDestroy(c->own);
+  delete c;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_stream(svgpu_ctx* c, void* s) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->st = s ? (cudaStream_t)s : c->own;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_reserve(svgpu_ctx* c, int maxBatch) {
+  if (!c || maxBatch < 1 || maxBatch > 1024) return fail(c, SV_INVALID_SETTINGS, "max_batch out of range");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  c->maxBatch = maxBatch;
+  if (c->haveSgbm) return ensure_scratch(c, maxBatch);
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_sync(svgpu_ctx* c) {
+  if (!c) return SV_INVALID_SETTINGS;
+  CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API const char* svgpu_last_error(const svgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+SVGPU_API int svgpu_set_rectify_maps(svgpu_ctx* c, int side, const int16_t* m1, const uint16_t* m2) {
+  if (!c || side < 0 || side > 1 || !m1 || !m2) return fail(c, SV_INVALID_SETTINGS, "bad rectify map arguments");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)c->W * c->H;
+  if (!c->map1[side]) CU(c, cudaMalloc((void**)&c->map1[side], n * 4));
+  if (!c->map2[side]) CU(c, cudaMalloc((void**)&c->map2[side], n * 2));
+  CU(c, cudaMemcpyAsync(c->map1[side], m1, n * 4, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->map2[side], m2, n * 2, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_Q(svgpu_ctx* c, const double Q[16]) {
+  if (!c || !Q) return fail(c, SV_INVALID_SETTINGS, "bad Q");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  CU(c, cudaMemcpyAsync(c->Qdev, Q, 16 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->haveQ = true;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_depth_consts(svgpu_ctx* c, float baseline, float focal) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->baseline = baseline; c->focal = focal; c->haveDepth = true;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_sgbm(svgpu_ctx* c, const svgpu_sgbm_params* p) {
+  if (!c || !p) return fail(c, SV_INVALID_SETTINGS, "null sgbm params");
+  std::lock_guard<std::mutex> lk(c->mu);
+  SgbmCfg g{};
+  int rc = normalise_sgbm(c, *p, g);
+  if (rc) return rc;
+  c->cfg = g; c->haveSgbm = true;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_sgbm_variant(svgpu_ctx* c, int variant) {
+  if (!c) return SV_INVALID_SETTINGS;
+  c->variant = variant;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_set_bm(svgpu_ctx* c, const svgpu_bm_params* p) {
+  if (!c || !p) return fail(c, SV_INVALID_SETTINGS, "null bm params");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (p->numDisparities <= 0 || p->numDisparities % 16 || p->numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "bm numDisparities must be a multiple of 16 in [16,256]");
+  if (p->blockSize < 5 || p->blockSize % 2 == 0 || p->blockSize > 51) return fail(c, SV_INVALID_SETTINGS, "bm blockSize must be odd in [5,51]");
+  if (p->preFilterCap < 1 || p->preFilterCap > 63) return fail(c, SV_INVALID_SETTINGS, "bm preFilterCap must be in [1,63]");
+  if (p->minDisparity != 0) return fail(c, SV_INVALID_SETTINGS, "bm minDisparity != 0 is not supported");
+  if (p->disp12MaxDiff >= 0) return fail(c, SV_INVALID_SETTINGS, "bm disp12MaxDiff >= 0 is not supported");
+  if ((long long)p->blockSize * p->blockSize * 2 * p->preFilterCap > 65535) return fail(c, SV_INVALID_SETTINGS, "bm blockSize^2*2*cap exceeds the 16-bit SAD range");
+  BmCfg b{};
+  b.W = c->W; b.H = c->H; b.D = p->numDisparities; b.minD = 0; b.bs = p->blockSize; b.cap = p->preFilterCap;
+  b.tex = p->textureThreshold; b.uniq = p->uniquenessRatio; b.d12 = p->disp12MaxDiff; b.filtered = (b.minD - 1) * 16;
+  b.speckleWindowSize = p->speckleWindowSize; b.speckleRange = p->speckleRange;
+  c->bm = b; c->haveBm = true;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_enable_stage_timing(svgpu_ctx* c, int on) {
+  if (!c) return SV_INVALID_SETTINGS;
+  c->timing = on != 0;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_last_stage_ms(svgpu_ctx* c, float ms[4]) {
+  if (!c || !ms) return SV_INVALID_SETTINGS;
+  if (!c->timing) return fail(c, SV_NOT_CONFIGURED, "stage timing is off");
+  CU(c, cudaEventSynchronize(c->ev[3]));
+  for (int i = 0; i < 3; i++) CU(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  CU(c, cudaEventElapsedTime(&ms[3], c->ev[0], c->ev[3]));
+  return SV_OK;
+}
+
+SVGPU_API long long svgpu_launch_count(const svgpu_ctx* c) { return c ? c->stats.launches : 0; }
+
+SVGPU_API int svgpu_remap(svgpu_ctx* c, int side, const uint8_t* src, int sw, int sh, size_t sstride, int cn, uint8_t* dst,
+                size_t dstride, int mem) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!src || !dst || sw <= 0 || sh <= 0) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (side < 0 || side > 1 || (cn != 1 && cn != 3)) return fail(c, SV_INVALID_SETTINGS, "bad side / channels");
+  if (!c->map1[side] || !c->map2[side]) return fail(c, SV_NOT_CONFIGURED, "rectify maps not set");
+  cudaSetDevice(c->device);
+  const uint8_t* ds = src; uint8_t* dd = dst; size_t dss = sstride, dds = dstride;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stSrc, (size_t)sw * sh * cn); if (rc) return rc;
+    rc = ensure(c, c->stRectL, (size_t)c->W * c->H * cn); if (rc) return rc;
+    rc = h2d_2d(c, c->stSrc.p, (size_t)sw * cn, src, sstride, (size_t)sw * cn, sh); if (rc) return rc;
+    ds = (const uint8_t*)c->stSrc.p; dss = (size_t)sw * cn; dd = (uint8_t*)c->stRectL.p; dds = (size_t)c->W * cn;
+  }
+  CU(c, launch_remap(ds, sw, sh, dss, cn, c->map1[side], c->map2[side], dd, c->W, c->H, dds, c->st));
+  c->stats.launches++;
+  if (mem == SV_MEM_HOST) {
+    int rc = d2h_2d(c, dst, dstride, dd, dds, (size_t)c->W * cn, c->H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_sgbm_compute(svgpu_ctx* c, const uint8_t* left, size_t ls, const uint8_t* right, size_t rs, int16_t* disp,
+                       size_t dstride, int mem) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!left || !right || !disp) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (!c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
+  cudaSetDevice(c->device);
+  const size_t W = c->W, H = c->H;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stLeft, W * H); if (rc) return rc;
+    rc = ensure(c, c->stRight, W * H); if (rc) return rc;
+    rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = h2d_2d(c, c->stLeft.p, W, left, ls, W, (int)H); if (rc) return rc;
+    rc = h2d_2d(c, c->stRight.p, W, right, rs, W, (int)H); if (rc) return rc;
+    rc = run_sgbm(c, 1, (uint8_t*)c->stLeft.p, W, W * H, (uint8_t*)c->stRight.p, W, W * H, (int16_t*)c->stDisp.p, W * 2, W * H * 2);
+    if (rc) return rc;
+    rc = d2h_2d(c, disp, dstride, c->stDisp.p, W * 2, W * 2, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+    return SV_OK;
+  }
+  return run_sgbm(c, 1, left, ls, 0, right, rs, 0, disp, dstride, 0);
+}
+
+SVGPU_API int svgpu_sgbm_compute_batch(svgpu_ctx* c, int n, const uint8_t* left, const uint8_t* right, int16_t* disp, int mem) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!left || !right || !disp || n <= 0) return fail(c, SV_INVALID_IMAGE, "empty batch");
+  if (!c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
+  cudaSetDevice(c->device);
+  const size_t W = c->W, H = c->H, img = W * H;
+  const int chunk = c->maxBatch;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stLeft, img * chunk); if (rc) return rc;
+    rc = ensure(c, c->stRight, img * chunk); if (rc) return rc;
+    rc = ensure(c, c->stDisp, img * 2 * chunk); if (rc) return rc;
+  }
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int m = std::min(chunk, n - f0);
+    if (mem == SV_MEM_HOST) {
+      CU(c, cudaMemcpyAsync(c->stLeft.p, left + f0 * img, img * m, cudaMemcpyHostToDevice, c->st));
+      CU(c, cudaMemcpyAsync(c->stRight.p, right + f0 * img, img * m, cudaMemcpyHostToDevice, c->st));
+      int rc = run_sgbm(c, m, (uint8_t*)c->stLeft.p, W, img, (uint8_t*)c->stRight.p, W, img, (int16_t*)c->stDisp.p, W * 2, img * 2);
+      if (rc) return rc;
+      CU(c, cudaMemcpyAsync(disp + f0 * img, c->stDisp.p, img * 2 * m, cudaMemcpyDeviceToHost, c->st));
+    } else {
+      int rc = run_sgbm(c, m, left + f0 * img, W, img, right + f0 * img, W, img, disp + f0 * img, W * 2, img * 2);
+      if (rc) return rc;
+    }
+  }
+  if (mem == SV_MEM_HOST) CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_bm_compute(svgpu_ctx* c, const uint8_t* left, size_t ls, const uint8_t* right, size_t rs, int16_t* disp,
+                     size_t dstride, int mem) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!left || !right || !disp) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (!c->haveBm) return fail(c, SV_NOT_CONFIGURED, "bm parameters not set");
+  cudaSetDevice(c->device);
+  const size_t W = c->W, H = c->H;
+  int rc = ensure(c, c->stBmL, W * H); if (rc) return rc;
+  rc = ensure(c, c->stBmR, W * H); if (rc) return rc;
+  const uint8_t *dl = left, *dr = right; int16_t* dd = disp; size_t dls = ls, drs = rs, dds = dstride;
+  if (mem == SV_MEM_HOST) {
+    rc = ensure(c, c->stLeft, W * H); if (rc) return rc;
+    rc = ensure(c, c->stRight, W * H); if (rc) return rc;
+    rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = h2d_2d(c, c->stLeft.p, W, left, ls, W, (int)H); if (rc) return rc;
+    rc = h2d_2d(c, c->stRight.p, W, right, rs, W, (int)H); if (rc) return rc;
+    dl = (uint8_t*)c->stLeft.p; dr = (uint8_t*)c->stRight.p; dd = (int16_t*)c->stDisp.p; dls = drs = W; dds = W * 2;
+  }
+  int nl = 0;
+  cudaError_t e = bm_forward(c->bm, dl, dls, dr, drs, (uint8_t*)c->stBmL.p, (uint8_t*)c->stBmR.p, dd, dds, c->st, &nl);
+  c->stats.launches += nl;
+  if (e != cudaSuccess) return cuda_fail(c, e, "bm_forward");
+  if (c->bm.speckleWindowSize > 0) {
+    rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;
+    rc = ensure(c, c->stSizes, W * H * 4); if (rc) return rc;
+    nl = 0;
+    e = launch_filter_speckles(dd, dds, c->W, c->H, c->bm.filtered, c->bm.speckleWindowSize, c->bm.speckleRange,
+                               (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl);
+    c->stats.launches += nl;
+    if (e != cudaSuccess) return cuda_fail(c, e, "filter_speckles");
+  }
+  if (mem == SV_MEM_HOST) {
+    rc = d2h_2d(c, disp, dstride, dd, dds, W * 2, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+// helper for the single-image int16 -> X stages below
+#define SV_STAGE_PROLOGUE()                                              \
+  if (!c) return SV_INVALID_SETTINGS;                                    \
+  std::lock_guard<std::mutex> lk(c->mu);                                 \
+  cudaSetDevice(c->device);                                              \
+  const size_t W = c->W, H = c->H;                                       \
+  (void)W; (void)H;
+
+SVGPU_API int svgpu_median3(svgpu_ctx* c, const int16_t* src, size_t ss, int16_t* dst, size_t dstride, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!src || !dst) return fail(c, SV_INVALID_IMAGE, "empty image");
+  const int16_t* s = src; int16_t* d = dst; size_t sss = ss, dds = dstride;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = ensure(c, c->stDisp2, W * H * 2); if (rc) return rc;
+    rc = h2d_2d(c, c->stDisp.p, W * 2, src, ss, W * 2, (int)H); if (rc) return rc;
+    s = (int16_t*)c->stDisp.p; d = (int16_t*)c->stDisp2.p; sss = dds = W * 2;
+  }
+  CU(c, launch_median3(s, sss, d, dds, c->W, c->H, 1, 0, 0, c->st));
+  c->stats.launches++;
+  if (mem == SV_MEM_HOST) {
+    int rc = d2h_2d(c, dst, dstride, d, dds, W * 2, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_filter_speckles(svgpu_ctx* c, int16_t* disp, size_t stride, int newVal, int maxSize, int maxDiff, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!disp) return fail(c, SV_INVALID_IMAGE, "empty image");
+  int rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;
+  rc = ensure(c, c->stSizes, W * H * 4); if (rc) return rc;
+  int16_t* d = disp; size_t ds = stride;
+  if (mem == SV_MEM_HOST) {
+    rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = h2d_2d(c, c->stDisp.p, W * 2, disp, stride, W * 2, (int)H); if (rc) return rc;
+    d = (int16_t*)c->stDisp.p; ds = W * 2;
+  }
+  int nl = 0;
+  cudaError_t e = launch_filter_speckles(d, ds, c->W, c->H, newVal, maxSize, maxDiff, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl);
+  c->stats.launches += nl;
+  if (e != cudaSuccess) return cuda_fail(c, e, "filter_speckles");
+  if (mem == SV_MEM_HOST) {
+    rc = d2h_2d(c, disp, stride, d, ds, W * 2, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_morph_close5(svgpu_ctx* c, const int16_t* src, size_t ss, int16_t* dst, size_t dstride, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!src || !dst) return fail(c, SV_INVALID_IMAGE, "empty image");
+  int rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;  // tmp plane
+  const int16_t* s = src; int16_t* d = dst; size_t sss = ss, dds = dstride;
+  if (mem == SV_MEM_HOST) {
+    rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = ensure(c, c->stDisp2, W * H * 2); if (rc) return rc;
+    rc = h2d_2d(c, c->stDisp.p, W * 2, src, ss, W * 2, (int)H); if (rc) return rc;
+    s = (int16_t*)c->stDisp.p; d = (int16_t*)c->stDisp2.p; sss = dds = W * 2;
+  }
+  CU(c, launch_morph_close5(s, sss, (int16_t*)c->stLabels.p, d, dds, c->W, c->H, c->st));
+  c->stats.launches += 2;
+  if (mem == SV_MEM_HOST) {
+    rc = d2h_2d(c, dst, dstride, d, dds, W * 2, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_reproject(svgpu_ctx* c, const int16_t* disp, size_t ds, float* xyz, size_t xs, int handleMissing, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!disp || !xyz) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (!c->haveQ) return fail(c, SV_NOT_CONFIGURED, "Q not set");
+  const int16_t* d = disp; float* o = xyz; size_t dds = ds, oos = xs;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = ensure(c, c->stXyz, W * H * 12); if (rc) return rc;
+    rc = h2d_2d(c, c->stDisp.p, W * 2, disp, ds, W * 2, (int)H); if (rc) return rc;
+    d = (int16_t*)c->stDisp.p; o = (float*)c->stXyz.p; dds = W * 2; oos = W * 12;
+  }
+  int nl = 0;
+  cudaError_t e = launch_reproject(d, dds, o, oos, c->W, c->H, c->Qdev, handleMissing, c->minScratch, c->st, &nl);
+  c->stats.launches += nl;
+  if (e != cudaSuccess) return cuda_fail(c, e, "reproject");
+  if (mem == SV_MEM_HOST) {
+    int rc = d2h_2d(c, xyz, xs, o, oos, W * 12, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_depth(svgpu_ctx* c, const int16_t* disp, size_t ds, float* depth, size_t zs, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!disp || !depth) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (!c->haveDepth) return fail(c, SV_NOT_CONFIGURED, "depth constants not set");
+  const int16_t* d = disp; float* o = depth; size_t dds = ds, oos = zs;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    rc = ensure(c, c->stDepth, W * H * 4); if (rc) return rc;
+    rc = h2d_2d(c, c->stDisp.p, W * 2, disp, ds, W * 2, (int)H); if (rc) return rc;
+    d = (int16_t*)c->stDisp.p; o = (float*)c->stDepth.p; dds = W * 2; oos = W * 4;
+  }
+  CU(c, launch_depth(d, dds, o, oos, c->W, c->H, c->baseline * c->focal, c->st));
+  c->stats.launches++;
+  if (mem == SV_MEM_HOST) {
+    int rc = d2h_2d(c, depth, zs, o, oos, W * 4, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_prefilter_chain(svgpu_ctx* c, const uint8_t* bgr, size_t bs, uint8_t* gray, size_t gs, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!bgr || !gray) return fail(c, SV_INVALID_IMAGE, "empty image");
+  int rc = ensure(c, c->stTmpH, W * H * 6); if (rc) return rc;
+  rc = ensure(c, c->stTmpG, W * H); if (rc) return rc;
+  const uint8_t* s = bgr; uint8_t* d = gray; size_t sss = bs, dds = gs;
+  if (mem == SV_MEM_HOST) {
+    rc = ensure(c, c->stRectL, W * H * 3); if (rc) return rc;
+    rc = ensure(c, c->stGrayL, W * H); if (rc) return rc;
+    rc = h2d_2d(c, c->stRectL.p, W * 3, bgr, bs, W * 3, (int)H); if (rc) return rc;
+    s = (uint8_t*)c->stRectL.p; d = (uint8_t*)c->stGrayL.p; sss = W * 3; dds = W;
+  }
+  CU(c, launch_prefilter_chain(s, sss, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, d, dds, c->W, c->H, c->st));
+  c->stats.launches += 3;
+  if (mem == SV_MEM_HOST) {
+    rc = d2h_2d(c, gray, gs, d, dds, W, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_resize(svgpu_ctx* c, const uint8_t* src, int sw, int sh, size_t ss, int cn, uint8_t* dst, size_t dstride, int mem) {
+  SV_STAGE_PROLOGUE();
+  if (!src || !dst || sw <= 0 || sh <= 0) return fail(c, SV_INVALID_IMAGE, "empty image");
+  if (cn != 1 && cn != 3) return fail(c, SV_INVALID_SETTINGS, "channels must be 1 or 3");
+  const uint8_t* s = src; uint8_t* d = dst; size_t sss = ss, dds = dstride;
+  if (mem == SV_MEM_HOST) {
+    int rc = ensure(c, c->stSrc, (size_t)sw * sh * cn); if (rc) return rc;
+    rc = ensure(c, c->stRectL, W * H * cn); if (rc) return rc;
+    rc = h2d_2d(c, c->stSrc.p, (size_t)sw * cn, src, ss, (size_t)sw * cn, sh); if (rc) return rc;
+    s = (uint8_t*)c->stSrc.p; d = (uint8_t*)c->stRectL.p; sss = (size_t)sw * cn; dds = W * cn;
+  }
+  CU(c, launch_resize(s, sw, sh, sss, cn, d, c->W, c->H, dds, c->st));
+  c->stats.launches++;
+  if (mem == SV_MEM_HOST) {
+    int rc = d2h_2d(c, dst, dstride, d, dds, W * cn, (int)H); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned stages) {
+  SV_STAGE_PROLOGUE();
+  if (!io || !io->left || !io->right) return fail(c, SV_INVALID_IMAGE, "empty image");
+  const int cn = io->channels;
+  if (cn != 1 && cn != 3) return fail(c, SV_INVALID_SETTINGS, "channels must be 1 or 3");
+  if ((stages & SV_STAGE_PREFILTER) && cn != 3) return fail(c, SV_INVALID_SETTINGS, "the pre-filter chain needs BGR input");
+  if (!(stages & SV_STAGE_PREFILTER) && (stages & SV_STAGE_SGBM) && cn != 1) return fail(c, SV_INVALID_SETTINGS, "SGBM without the pre-filter chain needs 8UC1 input");
+  if ((stages & SV_STAGE_SGBM) && !c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
+  if ((stages & SV_STAGE_REMAP) && (!c->map1[0] || !c->map1[1])) return fail(c, SV_NOT_CONFIGURED, "rectify maps not set");
+  if ((stages & SV_STAGE_REPROJECT) && !c->haveQ) return fail(c, SV_NOT_CONFIGURED, "Q not set");
+  if ((stages & SV_STAGE_DEPTH) && !c->haveDepth) return fail(c, SV_NOT_CONFIGURED, "depth constants not set");
+  if ((stages & (SV_STAGE_POSTFILTER | SV_STAGE_REPROJECT | SV_STAGE_DEPTH)) && !(stages & SV_STAGE_SGBM) && !io->disp)
+    return fail(c, SV_INVALID_IMAGE, "no disparity input");
+  const bool host = io->mem == SV_MEM_HOST;
+  int rc;
+  // current left/right images on the device
+  const uint8_t *curL = io->left, *curR = io->right;
+  size_t curLs = io->left_stride, curRs = io->right_stride;
+  if (host) {
+    rc = ensure(c, c->stLeft, W * H * cn); if (rc) return rc;
+    rc = ensure(c, c->stRight, W * H * cn); if (rc) return rc;
+    rc = h2d_2d(c, c->stLeft.p, W * cn, io->left, io->left_stride, W * cn, (int)H); if (rc) return rc;
+    rc = h2d_2d(c, c->stRight.p, W * cn, io->right, io->right_stride, W * cn, (int)H); if (rc) return rc;
+    curL = (uint8_t*)c->stLeft.p; curR = (uint8_t*)c->stRight.p; curLs = curRs = W * cn;
+  }
+  if (stages & SV_STAGE_REMAP) {
+    uint8_t *oL, *oR; size_t os;
+    if (!host && io->left_rect && io->right_rect) { oL = io->left_rect; oR = io->right_rect; os = io->rect_stride; }
+    else {
+      rc = ensure(c, c->stRectL, W * H * cn); if (rc) return rc;
+      rc = ensure(c, c->stRectR, W * H * cn); if (rc) return rc;
+      oL = (uint8_t*)c->stRectL.p; oR = (uint8_t*)c->stRectR.p; os = W * cn;
+    }
+    CU(c, launch_remap(curL, c->W, c->H, curLs, cn, c->map1[0], c->map2[0], oL, c->W, c->H, os, c->st));
+    CU(c, launch_remap(curR, c->W, c->H, curRs, cn, c->map1[1], c->map2[1], oR, c->W, c->H, os, c->st));
+    c->stats.launches += 2;
+    curL = oL; curR = oR; curLs = curRs = os;
+    if (host && io->left_rect) { rc = d2h_2d(c, io->left_rect, io->rect_stride, oL, os, W * cn, (int)H); if (rc) return rc; }
+    if (host && io->right_rect) { rc = d2h_2d(c, io->right_rect, io->rect_stride, oR, os, W * cn, (int)H); if (rc) return rc; }
+  }
+  if (stages & SV_STAGE_PREFILTER) {
+    rc = ensure(c, c->stTmpH, W * H * 6); if (rc) return rc;
+    rc = ensure(c, c->stTmpG, W * H); if (rc) return rc;
+    rc = ensure(c, c->stGrayL, W * H); if (rc) return rc;
+    rc = ensure(c, c->stGrayR, W * H); if (rc) return rc;
+    CU(c, launch_prefilter_chain(curL, curLs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayL.p, W, c->W, c->H, c->st));
+    CU(c, launch_prefilter_chain(curR, curRs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayR.p, W, c->W, c->H, c->st));
+    c->stats.launches += 6;
+    curL = (uint8_t*)c->stGrayL.p; curR = (uint8_t*)c->stGrayR.p; curLs = curRs = W;
+  }
+  int16_t* dd = io->disp; size_t dds = io->disp_stride;
+  if (host || !dd) {
+    rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
+    if (host && io->disp && !(stages & SV_STAGE_SGBM)) { rc = h2d_2d(c, c->stDisp.p, W * 2, io->disp, io->disp_stride, W * 2, (int)H); if (rc) return rc; }
+    dd = (int16_t*)c->stDisp.p; dds = W * 2;
+  }
+  if (stages & SV_STAGE_SGBM) {
+    rc = run_sgbm(c, 1, curL, curLs, 0, curR, curRs, 0, dd, dds, 0); if (rc) return rc;
+  }
+  if (stages & SV_STAGE_POSTFILTER) {
+    // src/lib.cpp:264 is a no-op for SGBM output (invalid = -16, never -1); :265 and :267-268 follow
+    rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;
+    rc = ensure(c, c->stSizes, W * H * 4); if (rc) return rc;
+    rc = ensure(c, c->stDisp2, W * H * 2); if (rc) return rc;
+    int nl = 0;
+    CU(c, launch_filter_speckles(dd, dds, c->W, c->H, 0, 150, 32, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl));
+    CU(c, launch_morph_close5(dd, dds, (int16_t*)c->stLabels.p, (int16_t*)c->stDisp2.p, W * 2, c->W, c->H, c->st));
+    CU(c, cudaMemcpy2DAsync(dd, dds, c->stDisp2.p, W * 2, W * 2, H, cudaMemcpyDeviceToDevice, c->st));
+    c->stats.launches += nl + 2;
+  }
+  if (host && io->disp && (stages & (SV_STAGE_SGBM | SV_STAGE_POSTFILTER))) {
+    rc = d2h_2d(c, io->disp, io->disp_stride, dd, dds, W * 2, (int)H); if (rc) return rc;
+  }
+  if ((stages & SV_STAGE_REPROJECT) && io->xyz) {
+    float* o = io->xyz; size_t os = io->xyz_stride;
+    if (host) { rc = ensure(c, c->stXyz, W * H * 12); if (rc) return rc; o = (float*)c->stXyz.p; os = W * 12; }
+    int nl = 0;
+    CU(c, launch_reproject(dd, dds, o, os, c->W, c->H, c->Qdev, 1, c->minScratch, c->st, &nl));
+    c->stats.launches += nl;
+    if (host) { rc = d2h_2d(c, io->xyz, io->xyz_stride, o, os, W * 12, (int)H); if (rc) return rc; }
+  }
+  if ((stages & SV_STAGE_DEPTH) && io->depth) {
+    float* o = io->depth; size_t os = io->depth_stride;
+    if (host) { rc = ensure(c, c->stDepth, W * H * 4); if (rc) return rc; o = (float*)c->stDepth.p; os = W * 4; }
+    CU(c, launch_depth(dd, dds, o, os, c->W, c->H, c->baseline * c->focal, c->st));
+    c->stats.launches++;
+    if (host) { rc = d2h_2d(c, io->depth, io->depth_stride, o, os, W * 4, (int)H); if (rc) return rc; }
+  }
+  if (host) CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_debug_copy_volume(svgpu_ctx* c, int which, int16_t* host, size_t bytes) {
+  SV_STAGE_PROLOGUE();
+  if (!host || !c->sc.C) return fail(c, SV_NOT_CONFIGURED, "no volume");
+  const size_t n = std::min(bytes, c->sc.frameCells * 2);
+  CU(c, cudaStreamSynchronize(c->st));
+  CU(c, cudaMemcpy(host, which == 0 ? c->sc.C : c->sc.S, n, cudaMemcpyDeviceToHost));
+  return SV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// common.cuh — shared declarations of the svgpu CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/svgpu.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "svgpu is written for sm_100a (B200) only"
+#endif
+
+namespace svgpu {
+
+// Normalised SGBM configuration as the kernels see it.
+struct SgbmCfg {
+  int W, H;          // image size
+  int D, minD;       // numDisparities, minDisparity
+  int minX1, W1;     // first computed column, number of computed columns
+  int P1, P2;        // normalised penalties
+  int uniq, d12;     // normalised uniquenessRatio, disp12MaxDiff
+  int ftzero;        // max(preFilterCap,15)|1
+  int r;             // blockSize/2
+  int mode;          // SV_MODE_*
+  int invalid;       // (minD-1)*16
+  int Wp;            // byte pitch of one pre-filter plane row
+  int speckleWindowSize, speckleRange;
+};
+
+struct BmCfg {
+  int W, H, D, minD, bs, cap, tex, uniq, d12, filtered;
+  int speckleWindowSize, speckleRange;
+};
+
+// Device buffers for `nframes` pairs in flight. Volumes are [frame][y][x'][d] uint16.
+struct SgbmScratch {
+  uint8_t* planesL;   // [frame][H][6][Wp]  g, glo, ghi, i, ilo, ihi
+  uint8_t* planesR;
+  uint16_t* C;        // cost volume Ctrue
+  uint16_t* S;        // aggregated volume
+  uint32_t* wtaKey;   // [frame][H][W1]  (minS<<16)|best or 0xFFFFFFFF
+  int16_t* dispRaw;   // [frame][H][W]   before / after LR check
+  int* status;        // device error flag (spin time-outs etc.)
+  unsigned long long* flags;  // inter-CTA progress flags of the sweep kernels
+  uint16_t* edges;    // inter-CTA edge exchange of the sweep kernels
+  size_t frameCells;  // W1*H*D
+};
+
+struct LaunchStats {
+  long long launches = 0;
+};
+
+// sgbm.cu
+cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
+                         size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int variant);
+size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
+size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
+
+// image_ops.cu
+cudaError_t launch_remap(const uint8_t* src, int sw, int sh, size_t sstride, int cn, const int16_t* map1,
+                         const uint16_t* map2, uint8_t* dst, int W, int H, size_t dstride, cudaStream_t st);
+cudaError_t launch_median3(const int16_t* src, size_t sstride, int16_t* dst, size_t dstride, int W, int H, int nframes,
+                           size_t sframe, size_t dframe, cudaStream_t st);
+cudaError_t launch_reproject(const int16_t* disp, size_t dstride, float* xyz, size_t xstride, int W, int H,
+                             const double* Qdev, int handleMissing, int* minScratch, cudaStream_t st, int* nlaunch);
+cudaError_t launch_depth(const int16_t* disp, size_t dstride, float* depth, size_t zstride, int W, int H, float bf,
+                         cudaStream_t st);
+cudaError_t launch_filter_speckles(int16_t* disp, size_t stride, int W, int H, int newVal, int maxSize, int maxDiff,
+                                   int* labels, int* sizes, int* changed, cudaStream_t st, int* nlaunch);
+cudaError_t launch_morph_close5(const int16_t* src, size_t sstride, int16_t* tmp, int16_t* dst, size_t dstride, int W,
+                                int H, cudaStream_t st);
+cudaError_t launch_prefilter_chain(const uint8_t* bgr, size_t bstride, uint16_t* tmpH, uint8_t* tmpGray, uint8_t* gray,
+                                   size_t gstride, int W, int H, cudaStream_t st);
+cudaError_t launch_resize(const uint8_t* src, int sw, int sh, size_t sstride, int cn, uint8_t* dst, int dw, int dh,
+                          size_t dstride, cudaStream_t st);
+
+// bm.cu
+cudaError_t bm_forward(const BmCfg& cfg, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
+                       uint8_t* pfL, uint8_t* pfR, int16_t* disp, size_t dstride, cudaStream_t st, int* nlaunch);
+
+}  // namespace svgpu

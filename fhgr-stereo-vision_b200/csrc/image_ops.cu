@@ -1,0 +1,310 @@
+// image_ops.cu — per-pixel stages around the SGBM core, sm_100a.
+// Each kernel replaces one OpenCV call of /root/reference/src/lib.cpp (cited per kernel);
+// arithmetic follows SURVEY.md Appendix A.7-A.13.  All of them are HBM-bound streaming
+// kernels: one thread per output pixel, coalesced rows, no shared-memory staging needed
+// beyond what L1/L2 give a 3x3 / 5x5 / 11-tap neighbourhood.
+#include "common.cuh"
+
+namespace svgpu {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+// ---- cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) with CV_16SC2 + CV_16UC1 maps — src/lib.cpp:89-92 (A.11)
+template <int CN>
+__global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+                                               const int16_t* __restrict__ map1, const uint16_t* __restrict__ map2,
+                                               uint8_t* __restrict__ dst, int W, int H, size_t dstride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const short2 m = ((const short2*)map1)[(size_t)y * W + x];
+  const int f = map2[(size_t)y * W + x] & 1023, fx = f & 31, fy = f >> 5;
+  const int x0 = m.x, y0 = m.y;
+  // 15-bit weights (32-fy)(32-fx)*32 ... are exact and always sum to 32768
+  const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+  const bool xin0 = x0 >= 0 && x0 < sw, xin1 = x0 + 1 >= 0 && x0 + 1 < sw;
+  const bool yin0 = y0 >= 0 && y0 < sh, yin1 = y0 + 1 >= 0 && y0 + 1 < sh;
+  const uint8_t* r0 = src + (size_t)y0 * sstride + (size_t)x0 * CN;
+  const uint8_t* r1 = r0 + sstride;
+  uint8_t* o = dst + (size_t)y * dstride + (size_t)x * CN;
+#pragma unroll
+  for (int c = 0; c < CN; c++) {
+    int acc = 16384;
+    if (yin0 && xin0) acc += w00 * r0[c];
+    if (yin0 && xin1) acc += w01 * r0[CN + c];
+    if (yin1 && xin0) acc += w10 * r1[c];
+    if (yin1 && xin1) acc += w11 * r1[CN + c];
+    o[c] = (uint8_t)min(acc >> 15, 255);
+  }
+}
+
+cudaError_t launch_remap(const uint8_t* src, int sw, int sh, size_t sstride, int cn, const int16_t* map1,
+                         const uint16_t* map2, uint8_t* dst, int W, int H, size_t dstride, cudaStream_t st) {
+  dim3 g((W + 255) / 256, H);
+  if (cn == 3) k_remap<3><<<g, 256, 0, st>>>(src, sw, sh, sstride, map1, map2, dst, W, H, dstride);
+  else k_remap<1><<<g, 256, 0, st>>>(src, sw, sh, sstride, map1, map2, dst, W, H, dstride);
+  return cudaGetLastError();
+}
+
+// ---- cv::medianBlur(CV_16S, 3), replicate border — last stage of StereoSGBM::compute (A.7)
+__device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
+__global__ void __launch_bounds__(256) k_median3(const int16_t* __restrict__ src, size_t sstride, size_t sframe,
+                                                 int16_t* __restrict__ dst, size_t dstride, size_t dframe, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const uint8_t* sb = (const uint8_t*)src + blockIdx.z * sframe;
+  const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+  const int16_t* r0 = (const int16_t*)(sb + (size_t)max(y - 1, 0) * sstride);
+  const int16_t* r1 = (const int16_t*)(sb + (size_t)y * sstride);
+  const int16_t* r2 = (const int16_t*)(sb + (size_t)min(y + 1, H - 1) * sstride);
+  int v0 = r0[xm], v1 = r0[x], v2 = r0[xp], v3 = r1[xm], v4 = r1[x], v5 = r1[xp], v6 = r2[xm], v7 = r2[x], v8 = r2[xp];
+  // 19-exchange median-of-9 network
+  cswap(v1, v2); cswap(v4, v5); cswap(v7, v8); cswap(v0, v1); cswap(v3, v4); cswap(v6, v7);
+  cswap(v1, v2); cswap(v4, v5); cswap(v7, v8); cswap(v0, v3); cswap(v5, v8); cswap(v4, v7);
+  cswap(v3, v6); cswap(v1, v4); cswap(v2, v5); cswap(v4, v7); cswap(v4, v2); cswap(v6, v4);
+  cswap(v4, v2);
+  *(int16_t*)((uint8_t*)dst + blockIdx.z * dframe + (size_t)y * dstride + (size_t)x * 2) = (int16_t)v4;
+}
+
+cudaError_t launch_median3(const int16_t* src, size_t sstride, int16_t* dst, size_t dstride, int W, int H, int nframes,
+                           size_t sframe, size_t dframe, cudaStream_t st) {
+  dim3 g((W + 255) / 256, H, nframes);
+  k_median3<<<g, 256, 0, st>>>(src, sstride, sframe, dst, dstride, dframe, W, H);
+  return cudaGetLastError();
+}
+
+// ---- cv::reprojectImageTo3D(disp CV_16S, Q, handleMissingValues) — src/lib.cpp:154 (A.12)
+__global__ void k_min_s16(const int16_t* __restrict__ disp, size_t dstride, int W, int H, int* out) {
+  int m = 32767;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const int16_t* r = (const int16_t*)((const uint8_t*)disp + (size_t)y * dstride);
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) m = min(m, (int)r[x]);
+  }
+  m = __reduce_min_sync(0xFFFFFFFFu, m);
+  if ((threadIdx.x & 31) == 0) atomicMin(out, m);
+}
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+__global__ void __launch_bounds__(256) k_reproject(const int16_t* __restrict__ disp, size_t dstride, float* __restrict__ xyz,
+                                                   size_t xstride, int W, int H, const double* __restrict__ Q,
+                                                   int handleMissing, const int* __restrict__ minDisp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int di = *(const int16_t*)((const uint8_t*)disp + (size_t)y * dstride + (size_t)x * 2);
+  const double d = (double)di;
+  double h[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) h[r] = Q[r * 4 + 0] * x + Q[r * 4 + 1] * y + Q[r * 4 + 2] * d + Q[r * 4 + 3];
+  float* o = (float*)((uint8_t*)xyz + (size_t)y * xstride) + (size_t)x * 3;
+  o[0] = (float)((double)(float)h[0] / h[3]);
+  o[1] = (float)((double)(float)h[1] / h[3]);
+  float z = (float)((double)(float)h[2] / h[3]);
+  if (handleMissing && di == *minDisp) z = 10000.f;
+  o[2] = z;
+}
+
+cudaError_t launch_reproject(const int16_t* disp, size_t dstride, float* xyz, size_t xstride, int W, int H,
+                             const double* Qdev, int handleMissing, int* minScratch, cudaStream_t st, int* nlaunch) {
+  if (handleMissing) {
+    k_set_int<<<1, 1, 0, st>>>(minScratch, 32767);
+    dim3 g(min((W + 255) / 256, 8), min(H, 148));
+    k_min_s16<<<g, 256, 0, st>>>(disp, dstride, W, H, minScratch);
+    *nlaunch += 2;
+  }
+  dim3 g((W + 255) / 256, H);
+  k_reproject<<<g, 256, 0, st>>>(disp, dstride, xyz, xstride, W, H, Qdev, handleMissing, minScratch);
+  *nlaunch += 1;
+  return cudaGetLastError();
+}
+
+// ---- StereoVision::CalculateDepthMapSimple — src/lib.cpp:279-294
+__global__ void __launch_bounds__(256) k_depth(const int16_t* __restrict__ disp, size_t dstride, float* __restrict__ depth,
+                                               size_t zstride, int W, int H, float bf) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int d = *(const int16_t*)((const uint8_t*)disp + (size_t)y * dstride + (size_t)x * 2);
+  *(float*)((uint8_t*)depth + (size_t)y * zstride + (size_t)x * 4) = d > 0 ? __fdiv_rn(bf, (float)d) : 0.0f;
+}
+cudaError_t launch_depth(const int16_t* disp, size_t dstride, float* depth, size_t zstride, int W, int H, float bf,
+                         cudaStream_t st) {
+  dim3 g((W + 255) / 256, H);
+  k_depth<<<g, 256, 0, st>>>(disp, dstride, depth, zstride, W, H, bf);
+  return cudaGetLastError();
+}
+
+// ---- cv::filterSpeckles(img, newVal, maxSpeckleSize, maxDiff) — src/lib.cpp:265 (A.8)
+// 4-connected components under the edge predicate |a-b| <= maxDiff (both != newVal) by lock-free
+// union-find on pixel indices, then a size histogram per root and a thresholded rewrite.
+__device__ __forceinline__ int uf_find(int* L, int i) {
+  int p = ((volatile int*)L)[i];
+  while (p != i) { i = p; p = ((volatile int*)L)[i]; }
+  return i;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  for (;;) {
+    a = uf_find(L, a); b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+__device__ __forceinline__ int px(const int16_t* img, size_t stride, int x, int y) {
+  return *(const int16_t*)((const uint8_t*)img + (size_t)y * stride + (size_t)x * 2);
+}
+__global__ void k_spk_init(const int16_t* img, size_t stride, int W, int H, int newVal, int* L, int* sizes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int i = y * W + x;
+  L[i] = px(img, stride, x, y) == newVal ? -1 : i;
+  sizes[i] = 0;
+}
+__global__ void k_spk_union(const int16_t* img, size_t stride, int W, int H, int newVal, int maxDiff, int* L) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int v = px(img, stride, x, y);
+  if (v == newVal) return;
+  const int i = y * W + x;
+  if (x > 0) { const int q = px(img, stride, x - 1, y); if (q != newVal && abs(v - q) <= maxDiff) uf_union(L, i, i - 1); }
+  if (y > 0) { const int q = px(img, stride, x, y - 1); if (q != newVal && abs(v - q) <= maxDiff) uf_union(L, i, i - W); }
+}
+__global__ void k_spk_count(int W, int H, int* L, int* sizes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int i = y * W + x;
+  if (L[i] < 0) return;
+  const int r = uf_find(L, i);
+  L[i] = r;  // path compression is safe here: no unions run concurrently
+  atomicAdd(&sizes[r], 1);
+}
+__global__ void k_spk_apply(int16_t* img, size_t stride, int W, int H, int newVal, int maxSize, const int* L, const int* sizes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int r = L[y * W + x];
+  if (r >= 0 && sizes[r] <= maxSize) *(int16_t*)((uint8_t*)img + (size_t)y * stride + (size_t)x * 2) = (int16_t)newVal;
+}
+cudaError_t launch_filter_speckles(int16_t* disp, size_t stride, int W, int H, int newVal, int maxSize, int maxDiff,
+                                   int* labels, int* sizes, int* /*changed*/, cudaStream_t st, int* nlaunch) {
+  dim3 g((W + 255) / 256, H);
+  k_spk_init<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, labels, sizes);
+  k_spk_union<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, maxDiff, labels);
+  k_spk_count<<<g, 256, 0, st>>>(W, H, labels, sizes);
+  k_spk_apply<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, maxSize, labels, sizes);
+  *nlaunch += 4;
+  return cudaGetLastError();
+}
+
+// ---- cv::morphologyEx(MORPH_CLOSE, 5x5 rect) on CV_16S — src/lib.cpp:267-268 (A.13)
+template <bool DILATE>
+__global__ void __launch_bounds__(256) k_morph5(const int16_t* __restrict__ src, size_t sstride, int16_t* __restrict__ dst,
+                                                size_t dstride, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  int v = DILATE ? -32768 : 32767;
+  for (int dy = -2; dy <= 2; dy++) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -2; dx <= 2; dx++) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const int s = px(src, sstride, xx, yy);
+      v = DILATE ? max(v, s) : min(v, s);
+    }
+  }
+  *(int16_t*)((uint8_t*)dst + (size_t)y * dstride + (size_t)x * 2) = (int16_t)v;
+}
+cudaError_t launch_morph_close5(const int16_t* src, size_t sstride, int16_t* tmp, int16_t* dst, size_t dstride, int W,
+                                int H, cudaStream_t st) {
+  dim3 g((W + 255) / 256, H);
+  k_morph5<true><<<g, 256, 0, st>>>(src, sstride, tmp, (size_t)W * 2, W, H);
+  k_morph5<false><<<g, 256, 0, st>>>(tmp, (size_t)W * 2, dst, dstride, W, H);
+  return cudaGetLastError();
+}
+
+// ---- GaussianBlur 11x11 s1.4 -> BGR2GRAY -> 3x3 sharpen — src/lib.cpp:231-246 (A.13)
+__constant__ int kGauss11[11] = {0, 1, 8, 26, 57, 72, 57, 26, 8, 1, 0};
+__global__ void __launch_bounds__(256) k_gauss_h(const uint8_t* __restrict__ bgr, size_t bstride, uint16_t* __restrict__ tmpH, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const uint8_t* r = bgr + (size_t)y * bstride;
+  int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int t = 1; t < 10; t++) {  // taps 0 and 10 are zero
+    const uint8_t* p = r + (size_t)reflect101(x + t - 5, W) * 3;
+    s0 += kGauss11[t] * p[0]; s1 += kGauss11[t] * p[1]; s2 += kGauss11[t] * p[2];
+  }
+  uint16_t* o = tmpH + ((size_t)y * W + x) * 3;
+  o[0] = (uint16_t)s0; o[1] = (uint16_t)s1; o[2] = (uint16_t)s2;
+}
+__global__ void __launch_bounds__(256) k_gauss_v_gray(const uint16_t* __restrict__ tmpH, uint8_t* __restrict__ gray, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int t = 1; t < 10; t++) {
+    const uint16_t* p = tmpH + ((size_t)reflect101(y + t - 5, H) * W + x) * 3;
+    s0 += kGauss11[t] * p[0]; s1 += kGauss11[t] * p[1]; s2 += kGauss11[t] * p[2];
+  }
+  const int b = (s0 + 32768u) >> 16, g = (s1 + 32768u) >> 16, r = (s2 + 32768u) >> 16;
+  gray[(size_t)y * W + x] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15);
+}
+__global__ void __launch_bounds__(256) k_sharpen3(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t dstride, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int c = src[(size_t)y * W + x];
+  const int l = src[(size_t)y * W + reflect101(x - 1, W)], r = src[(size_t)y * W + reflect101(x + 1, W)];
+  const int u = src[(size_t)reflect101(y - 1, H) * W + x], d = src[(size_t)reflect101(y + 1, H) * W + x];
+  dst[(size_t)y * dstride + x] = (uint8_t)min(max(5 * c - l - r - u - d, 0), 255);
+}
+cudaError_t launch_prefilter_chain(const uint8_t* bgr, size_t bstride, uint16_t* tmpH, uint8_t* tmpGray, uint8_t* gray,
+                                   size_t gstride, int W, int H, cudaStream_t st) {
+  dim3 g((W + 255) / 256, H);
+  k_gauss_h<<<g, 256, 0, st>>>(bgr, bstride, tmpH, W, H);
+  k_gauss_v_gray<<<g, 256, 0, st>>>(tmpH, tmpGray, W, H);
+  k_sharpen3<<<g, 256, 0, st>>>(tmpGray, gray, gstride, W, H);
+  return cudaGetLastError();
+}
+
+// ---- cv::resize(8U, INTER_LINEAR) — src/lib.cpp:102 (A.13), 11-bit fixed-point two-tap bilinear
+template <int CN>
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int sw, int sh, size_t sstride,
+                                                uint8_t* __restrict__ dst, int dw, int dh, size_t dstride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw) return;
+  const double sx = (double)sw / dw, sy = (double)sh / dh;
+  float fx = (float)((x + 0.5) * sx - 0.5);
+  int i0 = (int)floorf(fx);
+  fx -= i0;
+  if (i0 < 0) { i0 = 0; fx = 0; }
+  if (i0 >= sw - 1) { i0 = sw - 1; fx = 0; }
+  float fy = (float)((y + 0.5) * sy - 0.5);
+  int j0 = (int)floorf(fy);
+  fy -= j0;
+  if (j0 < 0) { j0 = 0; fy = 0; }
+  if (j0 >= sh - 1) { j0 = sh - 1; fy = 0; }
+  const int i1 = min(i0 + 1, sw - 1), j1 = min(j0 + 1, sh - 1);
+  const int a0 = __float2int_rn((1.f - fx) * 2048.f), a1 = __float2int_rn(fx * 2048.f);
+  const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
+  const uint8_t* r0 = src + (size_t)j0 * sstride;
+  const uint8_t* r1 = src + (size_t)j1 * sstride;
+  uint8_t* o = dst + (size_t)y * dstride + (size_t)x * CN;
+#pragma unroll
+  for (int c = 0; c < CN; c++) {
+    const int h0 = r0[i0 * CN + c] * a0 + r0[i1 * CN + c] * a1;
+    const int h1 = r1[i0 * CN + c] * a0 + r1[i1 * CN + c] * a1;
+    o[c] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+  }
+}
+cudaError_t launch_resize(const uint8_t* src, int sw, int sh, size_t sstride, int cn, uint8_t* dst, int dw, int dh,
+                          size_t dstride, cudaStream_t st) {
+  dim3 g((dw + 255) / 256, dh);
+  if (cn == 3) k_resize<3><<<g, 256, 0, st>>>(src, sw, sh, sstride, dst, dw, dh, dstride);
+  else k_resize<1><<<g, 256, 0, st>>>(src, sw, sh, sstride, dst, dw, dh, dstride);
+  return cudaGetLastError();
+}
+
+}  // namespace svgpu

@@ -1,0 +1,579 @@
+// sgbm.cu — semi-global block matching for sm_100a (B200).
+//
+// Replaces the call `stereo->compute(left_gray, right_gray, disparity)` at
+// /root/reference/src/lib.cpp:262 (cv::StereoSGBM, parameters :248-259).  OpenCV's
+// sources are not part of the reference tree; the arithmetic follows SURVEY.md
+// Appendix A.1-A.7, which tests/ check bit-exactly against the cv2 binary.
+//
+// Data layout in HBM (per pair in flight):
+//   planes  [y][6][Wp] u8      pre-filter rows of one image: g, lo(g), hi(g), i, lo(i), hi(i)
+//   C, S    [y][x'][d] u16     cost volume Ctrue and aggregated costs, d innermost so that one
+//                              pixel's D costs are D*2 contiguous bytes (256 B at D=128)
+//   wtaKey  [y][x']    u32     (minS<<16)|best of pixels that passed uniqueness, else ~0
+// Costs are kept as unsigned 16-bit lanes packed two per register; all min/add work
+// runs on the packed-SIMD integer instructions of sm_100 (VIMNMX.U16x2, VIMNMX3,
+// VIADDMNMX, VIADD.16x2) and __reduce_min_sync (CREDUX).
+#include "common.cuh"
+
+namespace svgpu {
+
+static constexpr uint32_t kMax2 = 0x7FFF7FFFu;  // two lanes of MAX_COST (32767)
+
+__device__ __forceinline__ uint32_t dup16(uint32_t v) { return v | (v << 16); }
+__device__ __forceinline__ uint32_t hmin16(uint32_t v) { return min(v & 0xFFFFu, v >> 16); }
+
+// ------------------------------------------------------------------------------------------------
+// K1: pre-filter planes (A.2) + Birchfield-Tomasi half-pixel bounds (A.3)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pf_grad(const uint8_t* r, const uint8_t* u, const uint8_t* d, int x, int W, int ftzero) {
+  if (x <= 0 || x >= W - 1) return ftzero;
+  int v = 2 * ((int)r[x + 1] - (int)r[x - 1]) + ((int)u[x + 1] - (int)u[x - 1]) + ((int)d[x + 1] - (int)d[x - 1]);
+  return min(max(v, -ftzero), ftzero) + ftzero;
+}
+__device__ __forceinline__ int pf_int(const uint8_t* r, int x, int W, int ftzero) {
+  return (x <= 0 || x >= W - 1) ? ftzero : (int)r[x];
+}
+
+__global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restrict__ left, size_t lstride, size_t lframe,
+                                                          const uint8_t* __restrict__ right, size_t rstride, size_t rframe,
+                                                          uint8_t* __restrict__ planesL, uint8_t* __restrict__ planesR,
+                                                          int W, int H, int Wp, int ftzero) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
+  if (x >= W) return;
+  const uint8_t* img = side ? right + frame * rframe : left + frame * lframe;
+  const size_t stride = side ? rstride : lstride;
+  const uint8_t* r = img + (size_t)y * stride;
+  const uint8_t* u = y > 0 ? r - stride : r;
+  const uint8_t* d = y < H - 1 ? r + stride : r;
+  const int g0 = pf_grad(r, u, d, x, W, ftzero), i0 = pf_int(r, x, W, ftzero);
+  int glo = g0, ghi = g0, ilo = i0, ihi = i0;
+  if (x > 0) {
+    const int g = (g0 + pf_grad(r, u, d, x - 1, W, ftzero)) >> 1, i = (i0 + pf_int(r, x - 1, W, ftzero)) >> 1;
+    glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
+  }
+  if (x < W - 1) {
+    const int g = (g0 + pf_grad(r, u, d, x + 1, W, ftzero)) >> 1, i = (i0 + pf_int(r, x + 1, W, ftzero)) >> 1;
+    glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
+  }
+  uint8_t* p = (side ? planesR : planesL) + ((size_t)frame * H + y) * 6 * Wp + x;
+  p[0] = (uint8_t)g0; p[Wp] = (uint8_t)glo; p[2 * Wp] = (uint8_t)ghi;
+  p[3 * Wp] = (uint8_t)i0; p[4 * Wp] = (uint8_t)ilo; p[5 * Wp] = (uint8_t)ihi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: pixel cost (A.3) + blockSize x blockSize box sum (A.4) -> Ctrue
+//   one CTA = TW output columns x a band of rows x all D; it walks down the band keeping the last
+//   2r+2 rows of pixel costs (u8) in a shared-memory ring and the running vertical sums Vs in
+//   shared memory; the horizontal window is summed from Vs.  Threads are (pixel slot, d-lane):
+//   a lane owns 8 consecutive disparities = 4 packed registers = one 16-byte store.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kCostTW = 32;
+static constexpr int kCostThreads = 256;
+
+struct CostSmem {
+  int NC, NR, NRp, RS;
+  size_t offLeft, offRA, offRB, offRing, offVs, total;
+};
+__host__ __device__ inline CostSmem cost_smem_layout(int D, int r) {
+  CostSmem s;
+  s.NC = kCostTW + 2 * r;
+  s.NR = s.NC + D - 1;
+  s.NRp = (s.NR + 3) & ~1;  // even, >= NR+1
+  s.RS = 2 * r + 2;
+  size_t o = 0;
+  s.offLeft = o; o += (size_t)s.NC * 6 * 4;
+  s.offRA = o; o += (size_t)6 * s.NRp * 2;
+  s.offRB = o; o += (size_t)6 * s.NRp * 2;
+  o = (o + 15) & ~(size_t)15;
+  s.offVs = o; o += (size_t)s.NC * D * 2;
+  s.offRing = o; o += (size_t)s.RS * s.NC * D;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t bt_pair(uint32_t u, uint32_t ulo, uint32_t uhi, uint32_t v, uint32_t vlo, uint32_t vhi) {
+  const uint32_t c0 = __vimax_s16x2_relu(__vsub2(u, vhi), __vsub2(vlo, u));
+  const uint32_t c1 = __vimax_s16x2_relu(__vsub2(v, uhi), __vsub2(ulo, v));
+  return __vminu2(c0, c1);
+}
+
+__global__ void __launch_bounds__(kCostThreads) k_cost_volume(const uint8_t* __restrict__ planesL,
+                                                              const uint8_t* __restrict__ planesR,
+                                                              uint16_t* __restrict__ Cvol, SgbmCfg cfg, int rowsPerBand,
+                                                              size_t frameCells) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int D = cfg.D, r = cfg.r, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
+  const CostSmem L = cost_smem_layout(D, r);
+  uint32_t* sLeft = (uint32_t*)(smem + L.offLeft);
+  uint16_t* sRA = (uint16_t*)(smem + L.offRA);
+  uint16_t* sRB = (uint16_t*)(smem + L.offRB);
+  uint16_t* sVs = (uint16_t*)(smem + L.offVs);
+  uint8_t* sRing = smem + L.offRing;
+  const int NC = L.NC, NR = L.NR, NRp = L.NRp, RS = L.RS;
+
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * kCostTW;  // first output column x' of the tile
+  const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
+  const uint8_t* pL = planesL + (size_t)frame * H * 6 * Wp;
+  const uint8_t* pR = planesR + (size_t)frame * H * 6 * Wp;
+  uint16_t* Cf = Cvol + (size_t)frame * frameCells;
+
+  const int G = D >> 3;                 // lanes per pixel
+  const int nslot = kCostThreads / G;   // pixel slots per CTA
+  const int slot = threadIdx.x / G, dl = threadIdx.x % G, d0 = dl * 8;
+  const bool live = slot < nslot;
+  // largest right-image x addressed by this tile; reversed index j = xrMax - xr = (NC-1-c) + d
+  const int xrMax = x0 + kCostTW - 1 + r + cfg.minX1 - cfg.minD;
+
+  for (int i = threadIdx.x; i < NC * (D >> 3); i += kCostThreads) ((uint4*)sVs)[i] = make_uint4(0, 0, 0, 0);
+
+  int last = -1;  // last image row whose pixel costs are in the ring
+  // rows [yb-1-r, yb-1+r] initialise Vs for the virtual row yb-1, then one row enters/leaves per step
+  for (int step = -(2 * r + 1); step < ye - yb; step++) {
+    const bool prologue = step < 0;
+    const int y = yb + step;  // output row (main loop only)
+    const int addRow = prologue ? min(max(yb - 1 - r + (step + 2 * r + 1), 0), H - 1) : min(y + r, H - 1);
+    const int subRow = prologue ? -1 : min(max(y - r - 1, 0), H - 1);
+    if (addRow > last || last < 0) {
+      // ---- stage the pre-filter planes of row addRow
+      __syncthreads();  // previous users of sLeft/sR are done
+      const int yr = (last < 0) ? addRow : last + 1;  // rows enter in order; (addRow == last+1 by construction)
+      const uint8_t* rowL = pL + (size_t)yr * 6 * Wp;
+      const uint8_t* rowR = pR + (size_t)yr * 6 * Wp;
+      for (int i = threadIdx.x; i < NC * 6; i += kCostThreads) {
+        const int c = i / 6, k = i % 6;
+        const int xp = x0 - r + c;
+        uint32_t v = 0;
+        if (xp >= 0 && xp < W1) v = rowL[(size_t)k * Wp + xp + cfg.minX1];
+        sLeft[i] = dup16(v);
+      }
+      for (int i = threadIdx.x; i < NR * 6; i += kCostThreads) {
+        const int k = i / NR, j = i % NR;
+        const int xr = xrMax - j;
+        uint16_t v = 0;
+        if (xr >= 0 && xr < cfg.W) v = rowR[(size_t)k * Wp + xr];
+        sRA[k * NRp + j] = v;
+        if (j > 0) sRB[k * NRp + j - 1] = v;
+      }
+      __syncthreads();
+      // ---- pixel costs of row yr for this thread's cells -> ring slot yr % RS
+      if (live) {
+        uint8_t* ring = sRing + (size_t)(yr % RS) * NC * D;
+        for (int c = slot; c < NC; c += nslot) {
+          const int xp = x0 - r + c;
+          if (xp < 0 || xp >= W1) continue;
+          const uint32_t* lp = sLeft + c * 6;
+          const uint32_t ug = lp[0], uglo = lp[1], ughi = lp[2], ui = lp[3], uilo = lp[4], uihi = lp[5];
+          const int j0 = (NC - 1 - c) + d0;
+          const uint32_t* rp = (const uint32_t*)((j0 & 1) ? sRB : sRA) + (j0 >> 1);
+          uint32_t pix[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint32_t cg = bt_pair(ug, uglo, ughi, rp[q], rp[(NRp >> 1) + q], rp[2 * (NRp >> 1) + q]);
+            const uint32_t ci = bt_pair(ui, uilo, uihi, rp[3 * (NRp >> 1) + q], rp[4 * (NRp >> 1) + q], rp[5 * (NRp >> 1) + q]);
+            pix[q] = cg + ((ci >> 2) & 0x3FFF3FFFu);
+          }
+          uint2 packed;
+          packed.x = __byte_perm(pix[0], pix[1], 0x6420);
+          packed.y = __byte_perm(pix[2], pix[3], 0x6420);
+          *(uint2*)(ring + (size_t)c * D + d0) = packed;
+        }
+      }
+      last = yr;
+    }
+    // ---- Vs += ring[addRow] - ring[subRow] for this thread's own cells (no barrier needed: same owner)
+    if (live) {
+      const uint8_t* ra = sRing + (size_t)(addRow % RS) * NC * D;
+      const uint8_t* rs = subRow >= 0 ? sRing + (size_t)(subRow % RS) * NC * D : nullptr;
+      for (int c = slot; c < NC; c += nslot) {
+        const int xp = x0 - r + c;
+        if (xp < 0 || xp >= W1) continue;
+        uint4* vp = (uint4*)(sVs + (size_t)c * D + d0);
+        uint4 v = *vp;
+        const uint2 a = *(const uint2*)(ra + (size_t)c * D + d0);
+        v.x += __byte_perm(a.x, 0, 0x4140); v.y += __byte_perm(a.x, 0, 0x4342);
+        v.z += __byte_perm(a.y, 0, 0x4140); v.w += __byte_perm(a.y, 0, 0x4342);
+        if (rs) {
+          const uint2 s = *(const uint2*)(rs + (size_t)c * D + d0);
+          v.x -= __byte_perm(s.x, 0, 0x4140); v.y -= __byte_perm(s.x, 0, 0x4342);
+          v.z -= __byte_perm(s.y, 0, 0x4140); v.w -= __byte_perm(s.y, 0, 0x4342);
+        }
+        *vp = v;
+      }
+    }
+    if (prologue) continue;
+    __syncthreads();
+    // ---- horizontal window over Vs (clamped in W1 coordinates, A.4) -> Ctrue[y][x'][d0..d0+7]
+    if (live) {
+      const bool hh4zero = (cfg.mode == SV_MODE_HH4) && (y >= H - r);
+      for (int t = slot; t < kCostTW; t += nslot) {
+        const int xp = x0 + t;
+        if (xp >= W1) break;
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        if (!hh4zero) {
+          for (int dx = -r; dx <= r; dx++) {
+            const int cc = min(max(xp + dx, 0), W1 - 1) - (x0 - r);
+            const uint4 v = *(const uint4*)(sVs + (size_t)cc * D + d0);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        }
+        *(uint4*)(Cf + ((size_t)y * W1 + xp) * D + d0) = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Path aggregation (A.5).  One min-plus step of one path for 8 disparities per lane.
+//   L      previous / next path costs of this lane (4 packed registers, u16x2)
+//   mdup   min over all d of the previous L, duplicated in both halves
+//   c      Ctrue of the current pixel
+// Neighbouring lanes exchange their border disparities with two shuffles; lanes beyond D hold
+// MAX_COST so that they act as the L(q,-1) = L(q,D) = 32767 boundary.
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __forceinline__ void sgm_step(uint32_t (&L)[4], uint32_t& mdup, const uint4& c, uint32_t p1dup,
+                                         uint32_t p2dup, unsigned gmask, int gl, bool active) {
+  uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[3], 1, LPP);
+  uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPP);
+  if (gl == 0) up = kMax2;
+  if (gl == LPP - 1) dn = kMax2;
+  const uint32_t mp2 = mdup + p2dup;
+  const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+  uint32_t prev = up, n[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t next = (i < 3) ? L[i + 1] : dn;
+    const uint32_t lm1 = __byte_perm(prev, L[i], 0x5432);  // L(q,d-1) for the pair
+    const uint32_t lp1 = __byte_perm(L[i], next, 0x5432);  // L(q,d+1)
+    uint32_t t = __viaddmin_u16x2(__vminu2(lm1, lp1), p1dup, mp2);
+    t = __vminu2(t, L[i]);
+    n[i] = __vadd2(t, __vsub2(cc[i], mdup));
+    prev = L[i];
+  }
+  uint32_t mn = __vminu2(__vminu2(n[0], n[1]), __vminu2(n[2], n[3]));
+#pragma unroll
+  for (int i = 0; i < 4; i++) L[i] = active ? n[i] : kMax2;
+  uint32_t m = active ? hmin16(mn) : 0x7FFFu;
+  m = __reduce_min_sync(gmask, m);
+  mdup = dup16(m);
+}
+
+// first pixel of a path: predecessor outside the volume, L = Ctrue
+__device__ __forceinline__ void sgm_first(uint32_t (&L)[4], uint32_t& mdup, const uint4& c, unsigned gmask, bool active) {
+  L[0] = active ? c.x : kMax2; L[1] = active ? c.y : kMax2; L[2] = active ? c.z : kMax2; L[3] = active ? c.w : kMax2;
+  uint32_t m = hmin16(__vminu2(__vminu2(L[0], L[1]), __vminu2(L[2], L[3])));
+  m = __reduce_min_sync(gmask, m);
+  mdup = dup16(m);
+}
+
+// K3 (variant 0): one group of LPP lanes walks one scan line of one path and accumulates into S.
+// Chains of a diagonal path start on the top/bottom row and on one side column.
+template <int LPP>
+__global__ void __launch_bounds__(128) k_agg_walk(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol,
+                                                  SgbmCfg cfg, int tx, int ty, int accumulate, int nchains,
+                                                  int nframes, size_t frameCells) {
+  const int D = cfg.D, W1 = cfg.W1, H = cfg.H;
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPP;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPP;
+  const unsigned gmask = (LPP == 32) ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (lane - gl));
+  const bool active = gl * 8 < D;
+  const int chain = gid % nchains, frame = gid / nchains;
+  int x, y, len = 0;
+  if (frame < nframes) {
+    if (ty == 0) { y = chain; x = tx > 0 ? 0 : W1 - 1; len = W1; }
+    else if (tx == 0) { x = chain; y = ty > 0 ? 0 : H - 1; len = H; }
+    else if (chain < W1) { x = chain; y = ty > 0 ? 0 : H - 1; len = min(H, tx > 0 ? W1 - x : x + 1); }
+    else { const int k = chain - W1; y = ty > 0 ? k + 1 : H - 2 - k; x = tx > 0 ? 0 : W1 - 1; len = min(W1, ty > 0 ? H - y : y + 1); }
+  } else { x = y = 0; }
+  // warp-uniform trip count so that the full-mask shuffles stay converged
+  int maxlen = len;
+#pragma unroll
+  for (int o = 16; o >= LPP && o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xFFFFFFFFu, maxlen, o));
+  if (LPP == 32) maxlen = len;
+
+  const long long stepEl = ((long long)ty * W1 + tx) * D;
+  const uint16_t* cp = Cvol + (size_t)frame * (frame < nframes ? frameCells : 0) + ((size_t)y * W1 + x) * D + gl * 8;
+  uint16_t* sp = Svol + (size_t)frame * (frame < nframes ? frameCells : 0) + ((size_t)y * W1 + x) * D + gl * 8;
+  const uint32_t p1dup = dup16(cfg.P1), p2dup = dup16(cfg.P2);
+
+  uint32_t L[4] = {kMax2, kMax2, kMax2, kMax2}, mdup = 0;
+  uint4 cnext = make_uint4(0, 0, 0, 0), snext = make_uint4(0, 0, 0, 0);
+  if (active && len > 0) {
+    cnext = *(const uint4*)cp;
+    if (accumulate) snext = *(const uint4*)sp;
+  }
+  for (int i = 0; i < maxlen; i++) {
+    const bool on = i < len;
+    const uint4 c = cnext, s = snext;
+    if (active && i + 1 < len) {
+      cnext = *(const uint4*)(cp + stepEl);
+      if (accumulate) snext = *(const uint4*)(sp + stepEl);
+    }
+    if (i == 0) sgm_first(L, mdup, c, gmask, active && on);
+    else sgm_step<LPP>(L, mdup, c, p1dup, p2dup, gmask, gl, active && on);
+    if (active && on) {
+      uint4 o;
+      if (accumulate) {
+        o.x = __viaddmin_u16x2(s.x, L[0], kMax2); o.y = __viaddmin_u16x2(s.y, L[1], kMax2);
+        o.z = __viaddmin_u16x2(s.z, L[2], kMax2); o.w = __viaddmin_u16x2(s.w, L[3], kMax2);
+      } else { o.x = L[0]; o.y = L[1]; o.z = L[2]; o.w = L[3]; }
+      *(uint4*)sp = o;
+    }
+    cp += stepEl; sp += stepEl;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: winner-take-all + uniqueness + sub-pixel (A.6, first half) for one pixel held by a lane group
+//   s = final S of the pixel (this lane's 8 disparities).  Returns the raw CV_16S value (or invalid)
+//   and the key (minS<<16)|best (or ~0) that feeds the left-right check.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pick16(const uint32_t (&s)[4], int e) {  // element e (0..7) of the lane
+  const uint32_t w = (e & 4) ? ((e & 2) ? s[3] : s[2]) : ((e & 2) ? s[1] : s[0]);
+  return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+template <int LPP>
+__device__ __forceinline__ void wta_pixel(const uint32_t (&s)[4], int gl, unsigned gmask, bool active,
+                                          const SgbmCfg& cfg, int& dispOut, uint32_t& keyOut) {
+  const int d0 = gl * 8;
+  uint32_t k = 0xFFFFFFFFu;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      k = min(k, (s[i] << 16) | (uint32_t)(d0 + 2 * i));
+      k = min(k, (s[i] & 0xFFFF0000u) | (uint32_t)(d0 + 2 * i + 1));
+    }
+  }
+  k = __reduce_min_sync(gmask, k);
+  const int minS = (int)(k >> 16), best = (int)(k & 0xFFFFu);
+  dispOut = cfg.invalid;
+  keyOut = 0xFFFFFFFFu;
+  // neighbours of the winner for the parabola (owners publish, everybody reduces)
+  const int e1 = best - 1, e2 = best + 1;
+  uint32_t vm = 0, vp = 0;
+  if (active && e1 >= d0 && e1 < d0 + 8) vm = pick16(s, e1 - d0);
+  if (active && e2 >= d0 && e2 < d0 + 8) vp = pick16(s, e2 - d0);
+  vm = __reduce_max_sync(gmask, vm);
+  vp = __reduce_max_sync(gmask, vp);
+  // uniqueness: any d with S[d]*(100-uniq) < minS*100 and |best-d| > 1 rejects the pixel
+  bool rej = false;
+  if (active) {
+    const int f = 100 - cfg.uniq, t = minS * 100;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int a = (int)(s[i] & 0xFFFFu), b = (int)(s[i] >> 16), da = d0 + 2 * i;
+      rej |= (a * f < t) && (abs(best - da) > 1);
+      rej |= (b * f < t) && (abs(best - da - 1) > 1);
+    }
+  }
+  const unsigned rejBallot = __ballot_sync(0xFFFFFFFFu, rej) & gmask;
+  if (minS >= 32767 || rejBallot) return;
+  int dfix = best * 16;
+  if (best > 0 && best < cfg.D - 1) {
+    const int den = max((int)vm + (int)vp - 2 * minS, 1);
+    dfix += (((int)vm - (int)vp) * 16 + den) / (den * 2);
+  }
+  dispOut = dfix + cfg.minD * 16;
+  keyOut = k;
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, uint32_t* __restrict__ wtaKey,
+                                             int16_t* __restrict__ dispRaw, SgbmCfg cfg, int nframes, size_t frameCells) {
+  const int lane = threadIdx.x & 31, gl = lane % LPP;
+  const unsigned gmask = (LPP == 32) ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (lane - gl));
+  const bool active = gl * 8 < cfg.D;
+  const long long npix = (long long)nframes * cfg.H * cfg.W1;
+  const long long groupsPerGrid = (long long)gridDim.x * blockDim.x / LPP;
+  long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
+  // warp-uniform loop: every group of the warp iterates the same number of times
+  const long long warpFirst = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LPP;
+  for (long long base = warpFirst; base < npix; base += groupsPerGrid, pix += groupsPerGrid) {
+    const bool on = pix < npix;
+    uint32_t s[4] = {kMax2, kMax2, kMax2, kMax2};
+    int frame = 0, y = 0, xp = 0;
+    if (on) {
+      frame = (int)(pix / ((long long)cfg.H * cfg.W1));
+      const long long rem = pix % ((long long)cfg.H * cfg.W1);
+      y = (int)(rem / cfg.W1); xp = (int)(rem % cfg.W1);
+      if (active) {
+        const uint4 v = *(const uint4*)(Svol + (size_t)frame * frameCells + ((size_t)y * cfg.W1 + xp) * cfg.D + gl * 8);
+        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+      }
+    }
+    int dsp; uint32_t key;
+    wta_pixel<LPP>(s, gl, gmask, active && on, cfg, dsp, key);
+    if (on && gl == 0) {
+      wtaKey[((size_t)frame * cfg.H + y) * cfg.W1 + xp] = key;
+      dispRaw[((size_t)frame * cfg.H + y) * cfg.W + xp + cfg.minX1] = (int16_t)dsp;
+    }
+  }
+}
+
+// K5: left-right consistency check of one image row (A.6, second half).  disp2 is rebuilt by a
+// scatter-min of (minS, W1-1-x') keys: lowest cost wins, ties go to the largest x' — the same
+// winner as OpenCV's right-to-left scan with a strict '>' test.
+__global__ void __launch_bounds__(256) k_lr_check(const uint32_t* __restrict__ wtaKey, int16_t* __restrict__ dispRaw, SgbmCfg cfg) {
+  extern __shared__ uint32_t sKey[];  // [W]
+  const int y = blockIdx.x, frame = blockIdx.y;
+  const int W = cfg.W, W1 = cfg.W1;
+  const uint32_t* keys = wtaKey + ((size_t)frame * cfg.H + y) * W1;
+  int16_t* dr = dispRaw + ((size_t)frame * cfg.H + y) * W;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) sKey[x] = 0xFFFFFFFFu;
+  __syncthreads();
+  for (int xp = threadIdx.x; xp < W1; xp += blockDim.x) {
+    const uint32_t k = keys[xp];
+    if (k == 0xFFFFFFFFu) continue;
+    const int best = (int)(k & 0xFFFFu);
+    const int x2 = xp + cfg.minX1 - best - cfg.minD;
+    atomicMin(&sKey[x2], (k & 0xFFFF0000u) | (uint32_t)(W1 - 1 - xp));
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    if (x < cfg.minX1 || x >= cfg.minX1 + W1) { dr[x] = (int16_t)cfg.invalid; continue; }
+    const int d1 = dr[x];
+    if (d1 == cfg.invalid) continue;
+    const int _d = d1 >> 4, d_ = (d1 + 15) >> 4, _x = x - _d, x_ = x - d_;
+    bool bad = true;
+    {
+      bool c = false;
+      if (_x >= 0 && _x < W) {
+        const uint32_t k = sKey[_x];
+        // disp2 holds best+minD of the winner, or (minD-1)*16 when nothing landed there
+        const int d2 = (k == 0xFFFFFFFFu) ? cfg.invalid : ((W1 - 1 - (int)(k & 0xFFFFu)) + cfg.minX1 - _x);
+        c = d2 >= cfg.minD && abs(d2 - _d) > cfg.d12;
+      }
+      bad = bad && c;
+    }
+    {
+      bool c = false;
+      if (x_ >= 0 && x_ < W) {
+        const uint32_t k = sKey[x_];
+        const int d2 = (k == 0xFFFFFFFFu) ? cfg.invalid : ((W1 - 1 - (int)(k & 0xFFFFu)) + cfg.minX1 - x_);
+        c = d2 >= cfg.minD && abs(d2 - d_) > cfg.d12;
+      }
+      bad = bad && c;
+    }
+    if (bad) dr[x] = (int16_t)cfg.invalid;
+  }
+}
+
+__global__ void k_fill_s16(int16_t* p, size_t n, int v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (int16_t)v;
+}
+__global__ void k_fill_rows_s16(int16_t* p, size_t stride, size_t frame, int W, int H, int v) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < W) *(int16_t*)((uint8_t*)p + blockIdx.z * frame + (size_t)y * stride + (size_t)x * 2) = (int16_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t sgbm_flags_bytes(const SgbmCfg&, int nframes) { return (size_t)nframes * 4096 * sizeof(unsigned long long); }
+size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) { return (size_t)nframes * 512 * 2 * 2 * 2 * cfg.D * sizeof(uint16_t); }
+
+template <typename F>
+static void with_lpp(int D, F&& f) {
+  const int v = D / 8;
+  if (v <= 2) f(std::integral_constant<int, 2>());
+  else if (v <= 4) f(std::integral_constant<int, 4>());
+  else if (v <= 8) f(std::integral_constant<int, 8>());
+  else if (v <= 16) f(std::integral_constant<int, 16>());
+  else f(std::integral_constant<int, 32>());
+}
+
+#define SV_RET(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
+#define SV_LAUNCHED() do { if (stats) stats->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+static cudaError_t launch_walk(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int tx, int ty, int accumulate,
+                               cudaStream_t st, LaunchStats* stats) {
+  const int nchains = ty == 0 ? cfg.H : (tx == 0 ? cfg.W1 : cfg.W1 + cfg.H - 1);
+  cudaError_t err = cudaSuccess;
+  with_lpp(cfg.D, [&](auto lpp) {
+    constexpr int LPP = decltype(lpp)::value;
+    const long long threads = (long long)nchains * nframes * LPP;
+    const int block = 128;
+    const int grid = (int)((threads + block - 1) / block);
+    k_agg_walk<LPP><<<grid, block, 0, st>>>(sc.C, sc.S, cfg, tx, ty, accumulate, nchains, nframes, sc.frameCells);
+    err = cudaGetLastError();
+  });
+  if (stats) stats->launches++;
+  return err;
+}
+
+cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
+                         size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int variant) {
+  (void)variant;
+  const int W = cfg.W, H = cfg.H;
+  if (cfg.W1 <= 0) {  // A.1: nothing computable, whole map invalid
+    dim3 g((W + 255) / 256, H, nframes);
+    k_fill_rows_s16<<<g, 256, 0, st>>>(disp, dstride, dframe, W, H, cfg.invalid);
+    SV_LAUNCHED();
+    return cudaSuccess;
+  }
+  if (ev) SV_RET(cudaEventRecord(ev[0], st));
+  {
+    dim3 g((W + 255) / 256, H, nframes * 2);
+    k_prefilter_planes<<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H,
+                                          cfg.Wp, cfg.ftzero);
+    SV_LAUNCHED();
+  }
+  {
+    const CostSmem L = cost_smem_layout(cfg.D, cfg.r);
+    static size_t configured = 0;
+    if (L.total > configured) {
+      SV_RET(cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      configured = L.total;
+    }
+    const int tiles = (cfg.W1 + kCostTW - 1) / kCostTW;
+    // enough bands to fill the GPU a few times over, but not so many that the 2r+1-row prologue dominates
+    int bands = (148 * 4 + tiles * nframes - 1) / (tiles * nframes);
+    bands = max(1, min(bands, (H + 31) / 32));
+    const int rowsPerBand = (H + bands - 1) / bands;
+    bands = (H + rowsPerBand - 1) / rowsPerBand;
+    dim3 g(tiles, bands, nframes);
+    k_cost_volume<<<g, kCostThreads, L.total, st>>>(sc.planesL, sc.planesR, sc.C, cfg, rowsPerBand, sc.frameCells);
+    SV_LAUNCHED();
+  }
+  if (ev) SV_RET(cudaEventRecord(ev[1], st));
+  {
+    // predecessor offsets of A.5, expressed as travel directions (tx,ty) = -offset
+    static const int sgbm5[5][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}};
+    static const int hh8[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+    static const int hh4[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+    const int(*dirs)[2] = cfg.mode == SV_MODE_SGBM ? sgbm5 : (cfg.mode == SV_MODE_HH ? hh8 : hh4);
+    const int nd = cfg.mode == SV_MODE_SGBM ? 5 : (cfg.mode == SV_MODE_HH ? 8 : 4);
+    for (int i = 0; i < nd; i++) SV_RET(launch_walk(cfg, sc, nframes, dirs[i][0], dirs[i][1], i > 0, st, stats));
+  }
+  if (ev) SV_RET(cudaEventRecord(ev[2], st));
+  {
+    cudaError_t err = cudaSuccess;
+    with_lpp(cfg.D, [&](auto lpp) {
+      constexpr int LPP = decltype(lpp)::value;
+      const long long npix = (long long)nframes * H * cfg.W1;
+      const int block = 256;
+      const long long want = (npix * LPP + block - 1) / block;
+      const int grid = (int)std::min<long long>(want, 148LL * 8 * 4);
+      k_wta<LPP><<<grid, block, 0, st>>>(sc.S, sc.wtaKey, sc.dispRaw, cfg, nframes, sc.frameCells);
+      err = cudaGetLastError();
+    });
+    if (stats) stats->launches++;
+    SV_RET(err);
+    dim3 g(H, nframes);
+    k_lr_check<<<g, 256, (size_t)W * sizeof(uint32_t), st>>>(sc.wtaKey, sc.dispRaw, cfg);
+    SV_LAUNCHED();
+    SV_RET(launch_median3(sc.dispRaw, (size_t)W * 2, disp, dstride, W, H, nframes, (size_t)W * H * 2, dframe, st));
+    if (stats) stats->launches++;
+  }
+  if (ev) SV_RET(cudaEventRecord(ev[3], st));
+  return cudaSuccess;
+}
+
+}  // namespace svgpu

@@ -1,0 +1,286 @@
+"""`Context`: a thin, typed wrapper of one `svgpu_ctx*`.
+
+Host images are numpy arrays (copied through the library's staging buffers), device
+images are torch CUDA tensors (passed by `data_ptr()`; torch is only the allocator and
+stream provider here).  Every method maps 1:1 onto a C-ABI entry point of
+include/svgpu.h, which in turn replaces one OpenCV call of the reference's
+src/lib.cpp (citations in the header).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+class Context:
+    def __init__(self, width, height, device=0):
+        self._lib = _abi.load()
+        self.width, self.height, self.device = int(width), int(height), int(device)
+        h = C.c_void_p()
+        rc = self._lib.svgpu_create(self.device, self.width, self.height, C.byref(h))
+        if rc != _abi.SV_OK:
+            raise _abi.SvgpuError(rc, "svgpu_create failed (no CUDA device of compute capability 10.x, or out of memory)")
+        self._h = h
+        self._keep = []
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.svgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != _abi.SV_OK:
+            raise _abi.SvgpuError(rc, self._lib.svgpu_last_error(self._h).decode())
+
+    @staticmethod
+    def _ptr(a):
+        return C.c_void_p(a.data_ptr()) if _is_tensor(a) else a.ctypes.data_as(C.c_void_p)
+
+    @staticmethod
+    def _mem(*arrays):
+        dev = [_is_tensor(a) for a in arrays if a is not None]
+        if any(dev) and not all(dev):
+            raise ValueError("mix of host (numpy) and device (torch) buffers")
+        return _abi.SV_MEM_DEVICE if dev and dev[0] else _abi.SV_MEM_HOST
+
+    @staticmethod
+    def _stride(a):
+        return int(a.stride(0) * a.element_size()) if _is_tensor(a) else int(a.strides[0])
+
+    def _out_like(self, ref, shape, dtype):
+        if _is_tensor(ref):
+            import torch
+            tdt = {np.int16: torch.int16, np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+            return torch.empty(shape, dtype=tdt, device=ref.device)
+        return np.empty(shape, dtype)
+
+    def _img(self, a, dtype=np.uint8):
+        if _is_tensor(a):
+            if not a.is_cuda or a.stride(-1) != 1 or (a.dim() == 3 and a.stride(1) != a.shape[2]):
+                raise ValueError("device images must be CUDA tensors with packed pixels")
+            return a
+        a = np.asarray(a)
+        if a.dtype != dtype:
+            raise TypeError(f"expected {dtype}, got {a.dtype}")
+        if a.size == 0:
+            raise _abi.SvgpuError(_abi.SV_INVALID_IMAGE, "empty image")
+        if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != a.shape[2] * a.itemsize):
+            a = np.ascontiguousarray(a)
+        return a
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.svgpu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def reserve(self, max_batch):
+        self._check(self._lib.svgpu_reserve(self._h, int(max_batch)))
+
+    def sync(self):
+        self._check(self._lib.svgpu_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.svgpu_launch_count(self._h))
+
+    # -- one-time state ------------------------------------------------------------------------
+    def set_rectify_maps(self, side, map1, map2):
+        """cv::initUndistortRectifyMap outputs (CV_16SC2 + CV_16UC1) — src/lib.cpp:39-46."""
+        m1 = np.ascontiguousarray(map1, np.int16)
+        m2 = np.ascontiguousarray(map2, np.uint16)
+        if m1.shape != (self.height, self.width, 2) or m2.shape != (self.height, self.width):
+            raise ValueError("map shapes must be (H,W,2) int16 and (H,W) uint16")
+        self._check(self._lib.svgpu_set_rectify_maps(self._h, int(side), self._ptr(m1), self._ptr(m2)))
+
+    def set_Q(self, Q):
+        q = np.ascontiguousarray(Q, np.float64).reshape(16)
+        self._check(self._lib.svgpu_set_Q(self._h, self._ptr(q)))
+
+    def set_depth_consts(self, baseline, focal):
+        self._check(self._lib.svgpu_set_depth_consts(self._h, float(baseline), float(focal)))
+
+    def set_sgbm(self, **kw):
+        """Fields = the cv::StereoSGBM setters at src/lib.cpp:249-259."""
+        p = _abi.SgbmParams(**kw)
+        self._check(self._lib.svgpu_set_sgbm(self._h, C.byref(p)))
+        self._sgbm = dict(kw)
+
+    def set_bm(self, **kw):
+        d = dict(minDisparity=0, numDisparities=64, blockSize=21, preFilterCap=31, textureThreshold=10,
+                 uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1)
+        d.update(kw)
+        p = _abi.BmParams(**d)
+        self._check(self._lib.svgpu_set_bm(self._h, C.byref(p)))
+
+    def set_sgbm_variant(self, v):
+        self._check(self._lib.svgpu_set_sgbm_variant(self._h, int(v)))
+
+    def enable_stage_timing(self, on=True):
+        self._check(self._lib.svgpu_enable_stage_timing(self._h, int(bool(on))))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self._lib.svgpu_last_stage_ms(self._h, ms))
+        return dict(cost=ms[0], aggregate=ms[1], select=ms[2], total=ms[3])
+
+    # -- stages --------------------------------------------------------------------------------
+    def remap(self, side, src):
+        """cv::remap(INTER_LINEAR) — src/lib.cpp:89-92."""
+        src = self._img(src)
+        cn = 1 if src.ndim == 2 else int(src.shape[2])
+        shape = (self.height, self.width) if src.ndim == 2 else (self.height, self.width, cn)
+        dst = self._out_like(src, shape, np.uint8)
+        self._check(self._lib.svgpu_remap(self._h, int(side), self._ptr(src), int(src.shape[1]), int(src.shape[0]),
+                                          self._stride(src), cn, self._ptr(dst), self._stride(dst), self._mem(src)))
+        return dst
+
+    def _pair(self, left, right):
+        left, right = self._img(left), self._img(right)
+        if tuple(left.shape) != (self.height, self.width) or tuple(right.shape) != (self.height, self.width):
+            raise ValueError("images must be 8UC1 of the context size")
+        return left, right
+
+    def sgbm(self, left, right):
+        """cv::StereoSGBM::compute — src/lib.cpp:262."""
+        left, right = self._pair(left, right)
+        disp = self._out_like(left, (self.height, self.width), np.int16)
+        self._check(self._lib.svgpu_sgbm_compute(self._h, self._ptr(left), self._stride(left), self._ptr(right),
+                                                 self._stride(right), self._ptr(disp), self._stride(disp),
+                                                 self._mem(left, right)))
+        return disp
+
+    def sgbm_batch(self, left, right, out=None):
+        """n tightly packed pairs [n][H][W]."""
+        if _is_tensor(left):
+            if not (left.is_contiguous() and right.is_contiguous()):
+                raise ValueError("batch tensors must be contiguous")
+        else:
+            left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+        n = int(left.shape[0])
+        if tuple(left.shape[1:]) != (self.height, self.width) or tuple(right.shape) != tuple(left.shape):
+            raise ValueError("batch must be [n][H][W] 8UC1")
+        disp = out if out is not None else self._out_like(left, (n, self.height, self.width), np.int16)
+        self._check(self._lib.svgpu_sgbm_compute_batch(self._h, n, self._ptr(left), self._ptr(right), self._ptr(disp),
+                                                       self._mem(left, right, disp)))
+        return disp
+
+    def bm(self, left, right):
+        """cv::StereoBM::compute — BASELINE config 2."""
+        left, right = self._pair(left, right)
+        disp = self._out_like(left, (self.height, self.width), np.int16)
+        self._check(self._lib.svgpu_bm_compute(self._h, self._ptr(left), self._stride(left), self._ptr(right),
+                                               self._stride(right), self._ptr(disp), self._stride(disp),
+                                               self._mem(left, right)))
+        return disp
+
+    def _s16(self, a):
+        a = self._img(a, np.int16)
+        if tuple(a.shape) != (self.height, self.width):
+            raise ValueError("disparity must be CV_16S of the context size")
+        return a
+
+    def median3(self, disp):
+        disp = self._s16(disp)
+        out = self._out_like(disp, (self.height, self.width), np.int16)
+        self._check(self._lib.svgpu_median3(self._h, self._ptr(disp), self._stride(disp), self._ptr(out),
+                                            self._stride(out), self._mem(disp)))
+        return out
+
+    def filter_speckles(self, disp, new_val, max_size, max_diff):
+        """cv::filterSpeckles — src/lib.cpp:265 (returns a filtered copy)."""
+        disp = self._s16(disp)
+        out = disp.clone() if _is_tensor(disp) else disp.copy()
+        self._check(self._lib.svgpu_filter_speckles(self._h, self._ptr(out), self._stride(out), int(new_val),
+                                                    int(max_size), int(max_diff), self._mem(out)))
+        return out
+
+    def morph_close5(self, disp):
+        """cv::morphologyEx(MORPH_CLOSE, 5x5) — src/lib.cpp:267-268."""
+        disp = self._s16(disp)
+        out = self._out_like(disp, (self.height, self.width), np.int16)
+        self._check(self._lib.svgpu_morph_close5(self._h, self._ptr(disp), self._stride(disp), self._ptr(out),
+                                                 self._stride(out), self._mem(disp)))
+        return out
+
+    def reproject(self, disp, handle_missing=True):
+        """cv::reprojectImageTo3D — src/lib.cpp:154."""
+        disp = self._s16(disp)
+        out = self._out_like(disp, (self.height, self.width, 3), np.float32)
+        self._check(self._lib.svgpu_reproject(self._h, self._ptr(disp), self._stride(disp), self._ptr(out),
+                                              self._stride(out), int(bool(handle_missing)), self._mem(disp)))
+        return out
+
+    def depth(self, disp):
+        """StereoVision::CalculateDepthMapSimple — src/lib.cpp:279-294."""
+        disp = self._s16(disp)
+        out = self._out_like(disp, (self.height, self.width), np.float32)
+        self._check(self._lib.svgpu_depth(self._h, self._ptr(disp), self._stride(disp), self._ptr(out),
+                                          self._stride(out), self._mem(disp)))
+        return out
+
+    def prefilter_chain(self, bgr):
+        """GaussianBlur 11x11 + BGR2GRAY + sharpen — src/lib.cpp:231-246."""
+        bgr = self._img(bgr)
+        if tuple(bgr.shape) != (self.height, self.width, 3):
+            raise ValueError("expected 8UC3 of the context size")
+        out = self._out_like(bgr, (self.height, self.width), np.uint8)
+        self._check(self._lib.svgpu_prefilter_chain(self._h, self._ptr(bgr), self._stride(bgr), self._ptr(out),
+                                                    self._stride(out), self._mem(bgr)))
+        return out
+
+    def resize(self, src):
+        """cv::resize(INTER_LINEAR) to the context size — src/lib.cpp:96-104."""
+        src = self._img(src)
+        cn = 1 if src.ndim == 2 else int(src.shape[2])
+        shape = (self.height, self.width) if src.ndim == 2 else (self.height, self.width, cn)
+        out = self._out_like(src, shape, np.uint8)
+        self._check(self._lib.svgpu_resize(self._h, self._ptr(src), int(src.shape[1]), int(src.shape[0]),
+                                           self._stride(src), cn, self._ptr(out), self._stride(out), self._mem(src)))
+        return out
+
+    def pipeline(self, left, right, stages, want_rect=False, want_xyz=False, want_depth=False):
+        """StereoVision::AnalyzeAndAnnotateImage (kSGBM) — src/lib.cpp:53-85, any subset of stages."""
+        left, right = self._img(left), self._img(right)
+        cn = 1 if left.ndim == 2 else int(left.shape[2])
+        H, W = self.height, self.width
+        io = _abi.PipelineIO()
+        io.left, io.right = self._ptr(left), self._ptr(right)
+        io.left_stride, io.right_stride, io.channels = self._stride(left), self._stride(right), cn
+        io.mem = self._mem(left, right)
+        out = {}
+        if want_rect:
+            shape = (H, W) if cn == 1 else (H, W, cn)
+            out["left_rect"], out["right_rect"] = self._out_like(left, shape, np.uint8), self._out_like(left, shape, np.uint8)
+            io.left_rect, io.right_rect = self._ptr(out["left_rect"]), self._ptr(out["right_rect"])
+            io.rect_stride = self._stride(out["left_rect"])
+        out["disp"] = self._out_like(left, (H, W), np.int16)
+        io.disp, io.disp_stride = self._ptr(out["disp"]), self._stride(out["disp"])
+        if want_xyz:
+            out["xyz"] = self._out_like(left, (H, W, 3), np.float32)
+            io.xyz, io.xyz_stride = self._ptr(out["xyz"]), self._stride(out["xyz"])
+        if want_depth:
+            out["depth"] = self._out_like(left, (H, W), np.float32)
+            io.depth, io.depth_stride = self._ptr(out["depth"]), self._stride(out["depth"])
+        self._check(self._lib.svgpu_pipeline(self._h, C.byref(io), int(stages)))
+        return out
+
+    def debug_volume(self, which, shape):
+        out = np.zeros(shape, np.int16)
+        self._check(self._lib.svgpu_debug_copy_volume(self._h, int(which), self._ptr(out), out.nbytes))
+        return out

@@ -66,6 +66,25 @@ def sgbm(left, right, **kw):
     return disp
 
 
+def sgbm_debug(left, right, **kw):
+    """sgbm() plus the oracle's Ctrue and S volumes ([H][W1][D] int16) for stage-by-stage diffs."""
+    left, right = _u8(left), _u8(right)
+    H, W = left.shape
+    D, minD = kw["numDisparities"], kw["minDisparity"]
+    W1 = (W + min(minD, 0)) - max(minD + D, 0)
+    Cv = np.zeros((H, max(W1, 0), D), np.int16)
+    Sv = np.zeros_like(Cv)
+    L = lib()
+    pc = C.c_void_p.in_dll(L, "svo_debug_C")
+    ps = C.c_void_p.in_dll(L, "svo_debug_S")
+    pc.value, ps.value = Cv.ctypes.data, Sv.ctypes.data
+    try:
+        disp = sgbm(left, right, **kw)
+    finally:
+        pc.value, ps.value = None, None
+    return disp, Cv, Sv
+
+
 def bm(left, right, **kw):
     """cv::StereoBM::compute — BASELINE config 2."""
     left, right = _u8(left), _u8(right)

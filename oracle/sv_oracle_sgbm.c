@@ -49,6 +49,11 @@ static inline int bt(int u, int v, int loL, int hiL, int loR, int hiR) {
   return imin(c0, c1);
 }
 
+/* test hooks: when non-NULL the oracle copies its cost volume Ctrue (= C - P2) and the aggregated S
+ * ([y][x'][d], int16) here so that GPU intermediates can be diffed stage by stage */
+int16_t* svo_debug_C = 0;
+int16_t* svo_debug_S = 0;
+
 int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, int lstride, int rstride,
                      const svo_sgbm_params* prm, int16_t* disp, int dstride) {
   /* A.1 parameter normalisation */
@@ -177,6 +182,8 @@ int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, in
     }
   }
   free(L);
+  if (svo_debug_C) for (size_t i = 0; i < ncell; i++) svo_debug_C[i] = (int16_t)(C[i] - P2);
+  if (svo_debug_S) memcpy(svo_debug_S, S, ncell * 2);
   free(C);
 
   /* A.6 WTA + uniqueness + sub-pixel + LR check */

@@ -1,0 +1,215 @@
+"""Generates the golden vectors under tests/golden/ from the OpenCV binary (cv2) that the
+reference links against, following the reference's own call sequence in
+/root/reference/src/lib.cpp.  Run in the build container (needs cv2 and /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  sgbm_small.npz   small 8UC1 pairs + cv2.StereoSGBM disparities for MODE_SGBM / MODE_HH / MODE_HH4
+  bm_small.npz     small pairs + cv2.StereoBM disparities
+  stages_small.npz median / filterSpeckles / morph close / remap / reproject / pre-filter chain / resize cases
+  bottle.npz       the reference's bottle pair (resources/test-images-v1) through the mirror of
+                   StereoVision::AnalyzeAndAnnotateImage with Algorithm::kSGBM (src/lib.cpp:53-85):
+                   rectified gray inputs of StereoSGBM, raw and post-filtered disparity, calibration
+                   products (maps are regenerated from the YAML values stored alongside)
+"""
+import hashlib
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "fhgr-stereo-vision_b200"))
+from svgpu.synth import synth_pair  # noqa: E402
+
+REF = "/root/reference"
+
+
+def cv_sgbm(l, r, k):
+    s = cv2.StereoSGBM_create(minDisparity=k["minDisparity"], numDisparities=k["numDisparities"], blockSize=k["blockSize"],
+                              P1=k["P1"], P2=k["P2"], disp12MaxDiff=k["disp12MaxDiff"], preFilterCap=k["preFilterCap"],
+                              uniquenessRatio=k["uniquenessRatio"], speckleWindowSize=k["speckleWindowSize"],
+                              speckleRange=k["speckleRange"], mode=k["mode"])
+    return s.compute(l, r)
+
+
+PARAM_SETS = [
+    dict(blockSize=7, P1=392, P2=1568, uniquenessRatio=15, preFilterCap=32, disp12MaxDiff=1, speckleWindowSize=0, speckleRange=0),
+    dict(blockSize=5, P1=200, P2=800, uniquenessRatio=10, preFilterCap=31, disp12MaxDiff=1, speckleWindowSize=0, speckleRange=0),
+    dict(blockSize=3, P1=8, P2=32, uniquenessRatio=0, preFilterCap=63, disp12MaxDiff=2, speckleWindowSize=0, speckleRange=0),
+    dict(blockSize=1, P1=0, P2=0, uniquenessRatio=-1, preFilterCap=0, disp12MaxDiff=0, speckleWindowSize=0, speckleRange=0),
+    dict(blockSize=7, P1=392, P2=1568, uniquenessRatio=15, preFilterCap=32, disp12MaxDiff=1, speckleWindowSize=60, speckleRange=2),
+]
+
+
+def sgbm_cases():
+    cases = []
+    rng = np.random.default_rng(1234)
+    for (H, W, D) in [(33, 100, 32), (48, 200, 64), (40, 300, 224), (21, 40, 48)]:
+        for kind in ("synth", "noise", "const"):
+            if kind == "synth":
+                l, r = synth_pair(H, W, D, seed=H)
+            elif kind == "noise":
+                l = rng.integers(0, 256, (H, W), dtype=np.uint8)
+                r = rng.integers(0, 256, (H, W), dtype=np.uint8)
+            else:
+                l = np.full((H, W), 77, np.uint8)
+                r = np.full((H, W), 77, np.uint8)
+            for mode in (0, 1, 3):
+                for pi, prm in enumerate(PARAM_SETS):
+                    for minD in ((0,) if kind != "synth" else (0, 4, -8)):
+                        if (pi in (2, 3, 4)) and (D == 224 or minD != 0):
+                            continue
+                        k = dict(minDisparity=minD, numDisparities=D, mode=mode, **prm)
+                        cases.append((l, r, k, cv_sgbm(l, r, k)))
+    return cases
+
+
+def save_sgbm(path):
+    cases = sgbm_cases()
+    out = {"n": np.int64(len(cases))}
+    keys = ["minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
+            "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode"]
+    for i, (l, r, k, d) in enumerate(cases):
+        out[f"l{i}"], out[f"r{i}"], out[f"d{i}"] = l, r, d
+        out[f"p{i}"] = np.array([k[x] for x in keys], np.int32)
+    np.savez_compressed(path, **out)
+    print("sgbm cases", len(cases), os.path.getsize(path))
+
+
+def save_bm(path):
+    out = {}
+    i = 0
+    for (H, W, D, bs, uq, tex, spk) in [(40, 120, 32, 9, 15, 10, 0), (41, 130, 48, 5, 0, 0, 0), (36, 120, 16, 21, 15, 500, 0),
+                                        (64, 200, 64, 21, 15, 10, 0), (35, 97, 16, 7, 5, 3, 0), (64, 200, 32, 11, 10, 10, 40)]:
+        for seed in range(2):
+            l, r = synth_pair(H, W, D, seed)
+            bm = cv2.StereoBM_create(D, bs)
+            bm.setUniquenessRatio(uq)
+            bm.setTextureThreshold(tex)
+            if spk:
+                bm.setSpeckleWindowSize(spk)
+                bm.setSpeckleRange(2)
+            out[f"l{i}"], out[f"r{i}"], out[f"d{i}"] = l, r, bm.compute(l, r)
+            out[f"p{i}"] = np.array([0, D, bs, 31, tex, uq, spk, 2 if spk else 0, -1], np.int32)
+            i += 1
+    out["n"] = np.int64(i)
+    np.savez_compressed(path, **out)
+    print("bm cases", i, os.path.getsize(path))
+
+
+def load_calib(path):
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    n = fs.getNode("calibration")
+    g = lambda k: n.getNode(k).mat()  # noqa: E731
+    sz = n.getNode("image_size")
+    size = (int(sz.at(0).real()), int(sz.at(1).real()))
+    return dict(size=size, Kl=g("camera_matrix_left"), Dl=g("dist_coeffs_left"), Kr=g("camera_matrix_right"),
+                Dr=g("dist_coeffs_right"), R=g("R"), T=g("T"))
+
+
+def rectify_products(cal):
+    """StereoVision::StereoVision — src/lib.cpp:29-47."""
+    size = cal["size"]
+    Rl, Rr, Pl, Pr, Q, _, _ = cv2.stereoRectify(cal["Kl"], cal["Dl"], cal["Kr"], cal["Dr"], size, cal["R"], cal["T"],
+                                                flags=cv2.CALIB_ZERO_DISPARITY, alpha=0, newImageSize=size)
+    ml = cv2.initUndistortRectifyMap(cal["Kl"], cal["Dl"], Rl, Pl, size, cv2.CV_16SC2)
+    mr = cv2.initUndistortRectifyMap(cal["Kr"], cal["Dr"], Rr, Pr, size, cv2.CV_16SC2)
+    return dict(Rl=Rl, Rr=Rr, Pl=Pl, Pr=Pr, Q=Q, ml=ml, mr=mr)
+
+
+def save_stages(path):
+    rng = np.random.default_rng(99)
+    out = {}
+    a = rng.integers(-16, 2000, (37, 53)).astype(np.int16)
+    out["median_in"], out["median_out"] = a, cv2.medianBlur(a, 3)
+    b = (rng.integers(0, 6, (30, 40)) * 40 - 16).astype(np.int16)
+    b = cv2.resize(b, (160, 120), interpolation=cv2.INTER_NEAREST)
+    out["spk_in"] = b
+    spk = [(0, 150, 32), (-16, 60, 32), (-16, 20, 2), (0, 5, 100)]
+    out["spk_params"] = np.array(spk, np.int32)
+    for i, (nv, ms, md) in enumerate(spk):
+        c = b.copy()
+        cv2.filterSpeckles(c, nv, ms, md)
+        out[f"spk_out{i}"] = c
+    out["close_out"] = cv2.morphologyEx(b, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (5, 5)))
+    # rectification of a small crop-sized camera: v1 calibration scaled to 160x120
+    cal = load_calib(f"{REF}/resources/calibration/v1/calibration.yml")
+    s = 0.25
+    for k in ("Kl", "Kr"):
+        cal[k] = cal[k].copy()
+        cal[k][:2] *= s
+    cal["size"] = (160, 120)
+    pr = rectify_products(cal)
+    for k in ("Kl", "Dl", "Kr", "Dr", "R", "T"):
+        out["cal_" + k] = cal[k]
+    for k in ("Rl", "Rr", "Pl", "Pr", "Q"):
+        out["rect_" + k] = pr[k]
+    out["map1_l"], out["map2_l"] = pr["ml"]
+    out["map1_r"], out["map2_r"] = pr["mr"]
+    img = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    out["remap_in"] = img
+    out["remap_out_l"] = cv2.remap(img, pr["ml"][0], pr["ml"][1], cv2.INTER_LINEAR)
+    out["remap_out_r_gray"] = cv2.remap(img[:, :, 0].copy(), pr["mr"][0], pr["mr"][1], cv2.INTER_LINEAR)
+    d = rng.integers(-16, 3000, (120, 160)).astype(np.int16)
+    out["reproj_in"] = d
+    out["reproj_out_hm"] = cv2.reprojectImageTo3D(d, pr["Q"], handleMissingValues=True)
+    out["reproj_out"] = cv2.reprojectImageTo3D(d, pr["Q"], handleMissingValues=False)
+    blur = cv2.GaussianBlur(img, (11, 11), 1.4)
+    gray = cv2.cvtColor(blur, cv2.COLOR_BGR2GRAY)
+    k = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32)
+    out["chain_blur"], out["chain_gray"], out["chain_sharp"] = blur, gray, cv2.filter2D(gray, -1, k)
+    src = rng.integers(0, 256, (333, 517, 3), dtype=np.uint8)
+    out["resize_in"], out["resize_out"] = src, cv2.resize(src, (160, 120), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(path, **out)
+    print("stages", os.path.getsize(path))
+
+
+def save_bottle(path):
+    """Config 1 of BASELINE.json: the reference's own pair through its own chain (mirror of src/lib.cpp)."""
+    cal = load_calib(f"{REF}/resources/calibration/v1/calibration.yml")
+    pr = rectify_products(cal)
+    size = cal["size"]
+    L = cv2.imread(f"{REF}/resources/test-images-v1/left/bottle_000.jpg")
+    R = cv2.imread(f"{REF}/resources/test-images-v1/right/bottle_000.jpg")
+    # RescaleImage (src/lib.cpp:96-104) + RectifyImages (:87-94)
+    Ls = cv2.resize(L, size, interpolation=cv2.INTER_LINEAR)
+    Rs = cv2.resize(R, size, interpolation=cv2.INTER_LINEAR)
+    Lr = cv2.remap(Ls, pr["ml"][0], pr["ml"][1], cv2.INTER_LINEAR)
+    Rr = cv2.remap(Rs, pr["mr"][0], pr["mr"][1], cv2.INTER_LINEAR)
+    # CalculateDisparityMapUsingSGBM (:228-277)
+    k = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32)
+    gl = cv2.filter2D(cv2.cvtColor(cv2.GaussianBlur(Lr, (11, 11), 1.4), cv2.COLOR_BGR2GRAY), -1, k)
+    gr = cv2.filter2D(cv2.cvtColor(cv2.GaussianBlur(Rr, (11, 11), 1.4), cv2.COLOR_BGR2GRAY), -1, k)
+    prm = dict(minDisparity=0, numDisparities=224, blockSize=7, P1=392, P2=1568, disp12MaxDiff=1, preFilterCap=32,
+               uniquenessRatio=15, speckleWindowSize=0, speckleRange=2, mode=cv2.StereoSGBM_MODE_HH4)
+    raw = cv_sgbm(gl, gr, prm)
+    post = raw.copy()
+    post[post == -1] = 0
+    cv2.filterSpeckles(post, 0, 150, 32)
+    post = cv2.morphologyEx(post, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (5, 5)))
+    xyz = cv2.reprojectImageTo3D(post, pr["Q"], handleMissingValues=True)  # :152-156
+    bf = np.float32(abs(cal["T"][0, 0])) * np.float32(cal["Kl"][0, 0])
+    depth = np.where(post > 0, bf / post.astype(np.float32), np.float32(0)).astype(np.float32)  # :279-294
+    out = dict(scaled_left=Ls, scaled_right=Rs, rect_left=Lr, rect_right=Rr, gray_left=gl, gray_right=gr, disp_raw=raw,
+               disp_post=post, Q=pr["Q"], xyz_sha256=np.frombuffer(hashlib.sha256(xyz.tobytes()).digest(), np.uint8),
+               depth_sha256=np.frombuffer(hashlib.sha256(depth.tobytes()).digest(), np.uint8),
+               xyz_rows=xyz[200:204].copy(), depth_rows=depth[200:204].copy(),
+               baseline=np.float32(abs(cal["T"][0, 0])), focal=np.float32(cal["Kl"][0, 0]))
+    for kk in ("Kl", "Dl", "Kr", "Dr", "R", "T"):
+        out["cal_" + kk] = cal[kk]
+    for kk in ("Rl", "Rr", "Pl", "Pr"):
+        out["rect_" + kk] = pr[kk]
+    np.savez_compressed(path, **out)
+    print("bottle", os.path.getsize(path), "raw sha", hashlib.sha256(raw.tobytes()).hexdigest()[:16],
+          "post sha", hashlib.sha256(post.tobytes()).hexdigest()[:16], "valid", float((raw >= 0).mean()))
+
+
+if __name__ == "__main__":
+    save_sgbm(os.path.join(HERE, "sgbm_small.npz"))
+    save_bm(os.path.join(HERE, "bm_small.npz"))
+    save_stages(os.path.join(HERE, "stages_small.npz"))
+    save_bottle(os.path.join(HERE, "bottle.npz"))
