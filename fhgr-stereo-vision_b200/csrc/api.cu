@@ -149,6 +149,11 @@ int d2h_2d(svgpu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitc
 
 int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const uint8_t* dr, size_t rs, size_t rf,
              int16_t* dd, size_t ds, size_t df) {
+  // cv::StereoSGBM::compute throws for MODE_SGBM / MODE_HH when the image is too narrow for the
+  // disparity range ('width - (minDisparity + numDisparities) > SADWindowSize/2'); MODE_HH4 returns an
+  // all-invalid map instead.  Same behaviour here, as an error code.
+  if (c->cfg.mode != SV_MODE_HH4 && c->W - (c->cfg.minD + c->cfg.D) <= c->cfg.r)
+    return fail(c, SV_INVALID_SETTINGS, "image too narrow for minDisparity + numDisparities and blockSize");
   int rc = ensure_scratch(c, std::max(n, c->maxBatch));
   if (rc) return rc;
   cudaError_t e = sgbm_forward(c->cfg, c->sc, n, dl, ls, lf, dr, rs, rf, dd, ds, df, c->st, &c->stats,
@@ -218,7 +223,14 @@ SVGPU_API int svgpu_destroy(svgpu_ctx* c) {
 SVGPU_API int svgpu_set_stream(svgpu_ctx* c, void* s) {
   if (!c) return SV_INVALID_SETTINGS;
   std::lock_guard<std::mutex> lk(c->mu);
-  c->st = s ? (cudaStream_t)s : c->own;
+  c->st = (cudaStream_t)s;
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_use_own_stream(svgpu_ctx* c) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->st = c->own;
   return SV_OK;
 }
 

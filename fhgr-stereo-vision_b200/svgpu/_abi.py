@@ -19,7 +19,7 @@ STAGE_REMAP, STAGE_PREFILTER, STAGE_SGBM, STAGE_POSTFILTER, STAGE_REPROJECT, STA
 
 # every symbol include/svgpu.h declares; tests check that the library exports all of them
 EXPORTS = (
-    "svgpu_create", "svgpu_destroy", "svgpu_set_stream", "svgpu_reserve", "svgpu_sync", "svgpu_last_error",
+    "svgpu_create", "svgpu_destroy", "svgpu_set_stream", "svgpu_use_own_stream", "svgpu_reserve", "svgpu_sync", "svgpu_last_error",
     "svgpu_version", "svgpu_set_rectify_maps", "svgpu_set_Q", "svgpu_set_depth_consts", "svgpu_set_sgbm",
     "svgpu_set_bm", "svgpu_remap", "svgpu_sgbm_compute", "svgpu_sgbm_compute_batch", "svgpu_bm_compute",
     "svgpu_median3", "svgpu_filter_speckles", "svgpu_morph_close5", "svgpu_reproject", "svgpu_depth",
@@ -73,6 +73,7 @@ def load():
         "svgpu_create": (i, [i, i, i, C.POINTER(vp)]),
         "svgpu_destroy": (i, [vp]),
         "svgpu_set_stream": (i, [vp, vp]),
+        "svgpu_use_own_stream": (i, [vp]),
         "svgpu_reserve": (i, [vp, i]),
         "svgpu_sync": (i, [vp]),
         "svgpu_last_error": (C.c_char_p, [vp]),

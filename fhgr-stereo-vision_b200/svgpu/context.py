@@ -87,7 +87,11 @@ class Context:
         return a
 
     def set_stream(self, cuda_stream):
-        self._check(self._lib.svgpu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on the caller's cudaStream_t handle (an int; 0 is the CUDA default stream)."""
+        self._check(self._lib.svgpu_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def use_own_stream(self):
+        self._check(self._lib.svgpu_use_own_stream(self._h))
 
     def reserve(self, max_batch):
         self._check(self._lib.svgpu_reserve(self._h, int(max_batch)))

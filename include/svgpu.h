@@ -85,8 +85,11 @@ typedef struct svgpu_bm_params {
  * of image_size width x height on CUDA device `device`. */
 SVGPU_API int svgpu_create(int device, int width, int height, svgpu_ctx** out);
 SVGPU_API int svgpu_destroy(svgpu_ctx* ctx);
-/* attach the caller's cudaStream_t (e.g. torch's current stream); NULL -> own stream */
+/* run all further work of this context on the caller's cudaStream_t (e.g. torch's current stream).
+ * The handle is taken literally: NULL is the CUDA default stream. svgpu_use_own_stream goes back to
+ * the context's private non-blocking stream (the state after svgpu_create). */
 SVGPU_API int svgpu_set_stream(svgpu_ctx* ctx, void* cuda_stream);
+SVGPU_API int svgpu_use_own_stream(svgpu_ctx* ctx);
 /* how many pairs the *_batch calls may keep in flight (scratch = C and S volumes per pair) */
 SVGPU_API int svgpu_reserve(svgpu_ctx* ctx, int max_batch);
 SVGPU_API int svgpu_sync(svgpu_ctx* ctx);

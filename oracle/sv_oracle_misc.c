@@ -287,40 +287,63 @@ int svo_bm_compute(const uint8_t* left, const uint8_t* right, int W, int H, int 
     for (int x = 0; x < W; x++) dr[x] = (int16_t)FILTERED;
   }
   const int xlo = minD + D - 1 + wsz2, xhi = W - wsz2, ylo = wsz2, yhi = H - wsz2;
-  int sadbuf[1024 + 2];
-  int* sad = sadbuf + 1;
-  for (int y = ylo; y < yhi; y++) {
-    int16_t* dr = (int16_t*)((uint8_t*)disp + (size_t)y * dstride);
-    for (int x = xlo; x < xhi; x++) {
-      int tsum = 0;
-      for (int j = -wsz2; j <= wsz2; j++)
-        for (int i = -wsz2; i <= wsz2; i++) tsum += abs(PL[(size_t)(y + j) * W + x + i] - cap);
-      int minsad = 0x7fffffff, mind = -1;
-      for (int k = 0; k < D; k++) { /* k ascending == disparity descending */
-        const int d = D - 1 - k + minD;
-        int s = 0;
-        for (int j = -wsz2; j <= wsz2; j++) {
-          const uint8_t* l = PL + (size_t)(y + j) * W + x;
-          const uint8_t* r = PR + (size_t)(y + j) * W + x - d;
-          for (int i = -wsz2; i <= wsz2; i++) s += abs(l[i] - r[i]);
+  if (xlo < xhi && ylo < yhi) {
+    /* SAD volume by one integral image per disparity: sadv[(y*W+x)*D + k], k ascending == disparity descending */
+    int* sadv = (int*)malloc((size_t)W * H * D * sizeof(int));
+    int* integ = (int*)malloc((size_t)(W + 1) * (H + 1) * sizeof(int));
+    int* tinteg = (int*)malloc((size_t)(W + 1) * (H + 1) * sizeof(int));
+    for (int k = -1; k < D; k++) { /* k == -1 builds the texture integral |PL - cap| */
+      const int d = D - 1 - k + minD;
+      for (int x = 0; x <= W; x++) integ[x] = 0;
+      for (int y = 0; y < H; y++) {
+        int run = 0;
+        integ[(size_t)(y + 1) * (W + 1)] = 0;
+        for (int x = 0; x < W; x++) {
+          int a;
+          if (k < 0) a = abs(PL[(size_t)y * W + x] - cap);
+          else a = (x - d >= 0 && x - d < W) ? abs(PL[(size_t)y * W + x] - PR[(size_t)y * W + x - d]) : 0;
+          run += a;
+          integ[(size_t)(y + 1) * (W + 1) + x + 1] = integ[(size_t)y * (W + 1) + x + 1] + run;
         }
-        sad[k] = s;
-        if (s < minsad) { minsad = s; mind = k; }
       }
-      if (tsum < p->textureThreshold) continue;
-      if (p->uniquenessRatio > 0) {
-        const int thresh = minsad + (minsad * p->uniquenessRatio / 100);
-        int k;
-        for (k = 0; k < D; k++)
-          if ((k < mind - 1 || k > mind + 1) && sad[k] <= thresh) break;
-        if (k < D) continue;
-      }
-      sad[-1] = sad[1];
-      sad[D] = sad[D - 2];
-      const int pp = sad[mind + 1], n = sad[mind - 1];
-      const int dd = pp + n - 2 * sad[mind] + abs(pp - n);
-      dr[x] = (int16_t)(((D - mind - 1 + minD) * 256 + (dd != 0 ? (pp - n) * 256 / dd : 0) + 15) >> 4);
+      if (k < 0) { memcpy(tinteg, integ, (size_t)(W + 1) * (H + 1) * sizeof(int)); continue; }
+      for (int y = ylo; y < yhi; y++)
+        for (int x = xlo; x < xhi; x++) {
+          const int x0 = x - wsz2, x1 = x + wsz2 + 1, y0 = y - wsz2, y1 = y + wsz2 + 1;
+          sadv[((size_t)y * W + x) * D + k] = integ[(size_t)y1 * (W + 1) + x1] - integ[(size_t)y0 * (W + 1) + x1] -
+                                              integ[(size_t)y1 * (W + 1) + x0] + integ[(size_t)y0 * (W + 1) + x0];
+        }
     }
+    int sadbuf[1024 + 2];
+    int* sad = sadbuf + 1;
+    for (int y = ylo; y < yhi; y++) {
+      int16_t* dr = (int16_t*)((uint8_t*)disp + (size_t)y * dstride);
+      for (int x = xlo; x < xhi; x++) {
+        const int x0 = x - wsz2, x1 = x + wsz2 + 1, y0 = y - wsz2, y1 = y + wsz2 + 1;
+        const int tsum = tinteg[(size_t)y1 * (W + 1) + x1] - tinteg[(size_t)y0 * (W + 1) + x1] -
+                         tinteg[(size_t)y1 * (W + 1) + x0] + tinteg[(size_t)y0 * (W + 1) + x0];
+        int minsad = 0x7fffffff, mind = -1;
+        for (int k = 0; k < D; k++) { /* first strict minimum scanning disparities downwards */
+          const int sv = sadv[((size_t)y * W + x) * D + k];
+          sad[k] = sv;
+          if (sv < minsad) { minsad = sv; mind = k; }
+        }
+        if (tsum < p->textureThreshold) continue;
+        if (p->uniquenessRatio > 0) {
+          const int thresh = minsad + (minsad * p->uniquenessRatio / 100);
+          int k;
+          for (k = 0; k < D; k++)
+            if ((k < mind - 1 || k > mind + 1) && sad[k] <= thresh) break;
+          if (k < D) continue;
+        }
+        sad[-1] = sad[1];
+        sad[D] = sad[D - 2];
+        const int pp = sad[mind + 1], n = sad[mind - 1];
+        const int dd = pp + n - 2 * sad[mind] + abs(pp - n);
+        dr[x] = (int16_t)(((D - mind - 1 + minD) * 256 + (dd != 0 ? (pp - n) * 256 / dd : 0) + 15) >> 4);
+      }
+    }
+    free(sadv); free(integ); free(tinteg);
   }
   free(PL);
   free(PR);

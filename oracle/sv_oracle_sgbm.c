@@ -70,6 +70,8 @@ int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, in
   const int mode = prm->mode;
   if (D <= 0 || D % 16 != 0 || D > 1024) return -2;
   if (mode != SVO_MODE_SGBM && mode != SVO_MODE_HH && mode != SVO_MODE_HH4) return -2;
+  /* cv2 raises for MODE_SGBM / MODE_HH when width - (minD + D) <= blockSize/2; MODE_HH4 does not */
+  if (mode != SVO_MODE_HH4 && W - (minD + D) <= bs / 2) return -2;
 
   for (int y = 0; y < H; y++) {
     int16_t* dr = (int16_t*)((uint8_t*)disp + (size_t)y * dstride);

@@ -63,6 +63,8 @@ def sgbm_cases():
                     for minD in ((0,) if kind != "synth" else (0, 4, -8)):
                         if (pi in (2, 3, 4)) and (D == 224 or minD != 0):
                             continue
+                        if W - (minD + D) <= (prm["blockSize"] // 2) and mode != 3:
+                            continue  # cv2 throws for MODE_SGBM / MODE_HH (stereosgbm.cpp:511); HH4 returns all-invalid
                         k = dict(minDisparity=minD, numDisparities=D, mode=mode, **prm)
                         cases.append((l, r, k, cv_sgbm(l, r, k)))
     return cases

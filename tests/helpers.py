@@ -1,0 +1,39 @@
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SGBM_KEYS = ["minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
+             "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode"]
+BM_KEYS = ["minDisparity", "numDisparities", "blockSize", "preFilterCap", "textureThreshold", "uniquenessRatio",
+           "speckleWindowSize", "speckleRange", "disp12MaxDiff"]
+
+_cache = {}
+
+
+def golden(name):
+    if name not in _cache:
+        _cache[name] = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return _cache[name]
+
+
+def sgbm_golden_cases():
+    g = golden("sgbm_small")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]
+
+
+def bm_golden_cases():
+    g = golden("bm_small")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(BM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]
+
+
+def nmismatch(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return int((a != b).sum())
+
+
+REF_PARAMS = dict(blockSize=7, P1=392, P2=1568, disp12MaxDiff=1, preFilterCap=32, uniquenessRatio=15,
+                  speckleWindowSize=0, speckleRange=0, minDisparity=0)

@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/svgpu.h via the ctypes
+binding), against the CPU oracle and the committed cv2 golden vectors.  Integer outputs must be
+bit-exact; float outputs are compared bit-for-bit too (stated tolerance: 0 ulp; the north star
+allows 1e-4 relative)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import REF_PARAMS, bm_golden_cases, golden, nmismatch, sgbm_golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def svgpu():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    import svgpu as m
+    m._abi.load()
+    return m
+
+
+def test_sgbm_golden_all_modes(svgpu):
+    for i, l, r, prm, want in sgbm_golden_cases():
+        with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
+            ctx.set_sgbm(**prm)
+            for variant in (0, 1):
+                ctx.set_sgbm_variant(variant)
+                assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, variant, prm)
+
+
+def test_sgbm_too_narrow_matches_reference_error(svgpu):
+    l = np.zeros((21, 40), np.uint8)
+    with svgpu.Context(40, 21) as ctx:
+        for mode in (0, 1):
+            ctx.set_sgbm(numDisparities=48, mode=mode, **REF_PARAMS)
+            with pytest.raises(svgpu.SvgpuError) as e:
+                ctx.sgbm(l, l)
+            assert e.value.code == svgpu._abi.SV_INVALID_SETTINGS
+        ctx.set_sgbm(numDisparities=48, mode=3, **REF_PARAMS)
+        assert (ctx.sgbm(l, l) == -16).all()
+
+
+def test_invalid_settings_and_images(svgpu):
+    with svgpu.Context(64, 48) as ctx:
+        for bad in (dict(numDisparities=24), dict(numDisparities=512), dict(numDisparities=32, mode=2),
+                    dict(numDisparities=32, blockSize=4), dict(numDisparities=32, P2=30000)):
+            prm = dict(REF_PARAMS, mode=1)
+            prm.update(bad)
+            with pytest.raises(svgpu.SvgpuError) as e:
+                ctx.set_sgbm(**prm)
+            assert e.value.code == svgpu._abi.SV_INVALID_SETTINGS
+        with pytest.raises(svgpu.SvgpuError) as e:  # stage before its parameters
+            ctx.sgbm(np.zeros((48, 64), np.uint8), np.zeros((48, 64), np.uint8))
+        assert e.value.code == svgpu._abi.SV_NOT_CONFIGURED
+        with pytest.raises(svgpu.SvgpuError) as e:  # empty image -> kInvalidImage (src/lib.cpp:54-56)
+            ctx.remap(0, np.zeros((0, 0, 3), np.uint8))
+        assert e.value.code == svgpu._abi.SV_INVALID_IMAGE
+
+
+def test_bm_golden(svgpu):
+    for i, l, r, prm, want in bm_golden_cases():
+        with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
+            ctx.set_bm(**prm)
+            assert nmismatch(ctx.bm(l, r), want) == 0, (i, prm)
+
+
+def test_stages_golden(svgpu):
+    g = golden("stages_small")
+    with svgpu.Context(53, 37) as ctx:
+        assert nmismatch(ctx.median3(g["median_in"]), g["median_out"]) == 0
+    with svgpu.Context(160, 120) as ctx:
+        for i, (nv, ms, md) in enumerate(g["spk_params"]):
+            assert nmismatch(ctx.filter_speckles(g["spk_in"], nv, ms, md), g[f"spk_out{i}"]) == 0
+        assert nmismatch(ctx.morph_close5(g["spk_in"]), g["close_out"]) == 0
+        ctx.set_rectify_maps(0, g["map1_l"], g["map2_l"])
+        ctx.set_rectify_maps(1, g["map1_r"], g["map2_r"])
+        assert nmismatch(ctx.remap(0, g["remap_in"]), g["remap_out_l"]) == 0  # stated tolerance <= 1 LSB; achieved 0
+        assert nmismatch(ctx.remap(1, g["remap_in"][:, :, 0].copy()), g["remap_out_r_gray"]) == 0
+        ctx.set_Q(g["rect_Q"])
+        for hm, key in ((True, "reproj_out_hm"), (False, "reproj_out")):
+            got = ctx.reproject(g["reproj_in"], hm)
+            assert nmismatch(got.view(np.uint32), g[key].view(np.uint32)) == 0
+        assert nmismatch(ctx.prefilter_chain(g["remap_in"]), g["chain_sharp"]) == 0
+        assert nmismatch(ctx.resize(g["resize_in"]), g["resize_out"]) == 0
+
+
+def test_bottle_pair_full_chain(svgpu, oracle):
+    """BASELINE config 1 on the GPU: scaled frames -> rectify -> blur/gray/sharpen -> SGBM HH4 D=224 ->
+    filterSpeckles -> close -> XYZ + depth, one svgpu_pipeline call (src/lib.cpp:53-85)."""
+    g = golden("bottle")
+    size = (640, 480)
+    ml = oracle.init_undistort_rectify_map(g["cal_Kl"], g["cal_Dl"], g["rect_Rl"], g["rect_Pl"], size)
+    mr = oracle.init_undistort_rectify_map(g["cal_Kr"], g["cal_Dr"], g["rect_Rr"], g["rect_Pr"], size)
+    with svgpu.Context(*size) as ctx:
+        ctx.set_rectify_maps(0, *ml)
+        ctx.set_rectify_maps(1, *mr)
+        ctx.set_Q(g["Q"])
+        ctx.set_depth_consts(float(g["baseline"]), float(g["focal"]))
+        ctx.set_sgbm(**svgpu.REFERENCE_SGBM)
+        raw = ctx.pipeline(g["scaled_left"], g["scaled_right"], svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM,
+                           want_rect=True)
+        assert nmismatch(raw["left_rect"], g["rect_left"]) == 0 and nmismatch(raw["right_rect"], g["rect_right"]) == 0
+        assert nmismatch(raw["disp"], g["disp_raw"]) == 0
+        assert hashlib.sha256(np.ascontiguousarray(raw["disp"]).tobytes()).hexdigest()[:16] == "90f4df78b9ec67a4"
+        full = ctx.pipeline(g["scaled_left"], g["scaled_right"],
+                            svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM | svgpu.STAGE_POSTFILTER |
+                            svgpu.STAGE_REPROJECT | svgpu.STAGE_DEPTH, want_xyz=True, want_depth=True)
+        assert nmismatch(full["disp"], g["disp_post"]) == 0
+        assert hashlib.sha256(full["xyz"].tobytes()).digest() == g["xyz_sha256"].tobytes()
+        assert hashlib.sha256(full["depth"].tobytes()).digest() == g["depth_sha256"].tobytes()
+
+
+def test_device_memory_and_batch(svgpu, oracle):
+    import torch
+    from svgpu.synth import synth_batch
+    H, W, D, n = 60, 256, 64, 5
+    L, R = synth_batch(n, H, W, D, seed0=40)
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    want = np.stack([oracle.sgbm(L[i], R[i], **prm) for i in range(n)])
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**prm)
+        ctx.reserve(3)  # forces two chunks (3 + 2)
+        assert nmismatch(ctx.sgbm_batch(L, R), want) == 0  # host buffers
+        tl, tr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for variant in (0, 1):
+            ctx.set_sgbm_variant(variant)
+            td = ctx.sgbm_batch(tl, tr)
+            torch.cuda.synchronize()
+            assert nmismatch(td.cpu().numpy(), want) == 0, variant
+        one = ctx.sgbm(tl[2], tr[2])
+        torch.cuda.synchronize()
+        assert nmismatch(one.cpu().numpy(), want[2]) == 0
+        assert ctx.launch_count > 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_config2_720p_64_bit_exact(svgpu, oracle, mode):
+    """BASELINE config 2 (1280x720, 64 disparities): SGBM 5-path bit-exact; 8-path and HH4 ride along."""
+    from svgpu.synth import synth_pair
+    l, r = synth_pair(720, 1280, 64, seed=2)
+    prm = dict(REF_PARAMS, numDisparities=64, mode=mode)
+    want = oracle.sgbm(l, r, **prm)
+    with svgpu.Context(1280, 720) as ctx:
+        ctx.set_sgbm(**prm)
+        assert nmismatch(ctx.sgbm(l, r), want) == 0
+    assert (want[:, 64:] >= 0).mean() > 0.9
+
+
+def test_config2_720p_64_stereobm(svgpu, oracle):
+    from svgpu.synth import synth_pair
+    l, r = synth_pair(720, 1280, 64, seed=2)
+    with svgpu.Context(1280, 720) as ctx:
+        ctx.set_bm(numDisparities=64, blockSize=21)
+        assert nmismatch(ctx.bm(l, r), oracle.bm(l, r, numDisparities=64, blockSize=21)) == 0
+
+
+def test_config3_1080p_128_hh_bit_exact_and_properties(svgpu, oracle):
+    """BASELINE config 3 (1920x1080, 128 disparities, MODE_HH + LR check): one pair against the oracle at
+    full size, plus size-independent properties on a batch: determinism, batch == single, and saturation
+    behaviour on uncorrelated noise (every pixel whose S saturates is invalid)."""
+    import torch
+    from svgpu.synth import synth_batch
+    H, W, D = 1080, 1920, 128
+    L, R = synth_batch(3, H, W, D, seed0=10)
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**prm)
+        ctx.reserve(3)
+        tl, tr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        a = ctx.sgbm_batch(tl, tr).cpu().numpy()
+        b = ctx.sgbm_batch(tl, tr).cpu().numpy()
+        assert nmismatch(a, b) == 0
+        single = ctx.sgbm(L[1], R[1])
+        assert nmismatch(single, a[1]) == 0
+        assert nmismatch(a[0], oracle.sgbm(L[0], R[0], **prm)) == 0
+        assert (a[:, :, :D] == -16).all() and (a[:, :, D:] >= 0).mean() > 0.99
+        rng = np.random.default_rng(5)
+        nl, nr = rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+        dn = ctx.sgbm(nl, nr)
+        assert (dn >= 0).mean() < 0.2  # noise: S saturates almost everywhere -> invalid (A.6)
+
+
+def test_config4_4k_256_pipeline_matches_oracle_rows(svgpu, oracle):
+    """BASELINE config 4 (3840x2160, 256 disparities, rectify -> SGBM -> reprojectImageTo3D). The oracle is
+    too slow for the full 4K volume in a unit test, so the disparity is checked against the oracle on a
+    full-width horizontal band (rows are only coupled through the box window and the vertical/diagonal
+    paths, so MODE_HH4 restricted to a band is not comparable; instead the band is run as its own image on
+    both sides), and remap / reproject are checked at full 4K."""
+    from svgpu.synth import synth_pair
+    H, W, D = 2160, 3840, 256
+    l, r = synth_pair(H, W, D, seed=4)
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    band = slice(1000, 1048)
+    want = oracle.sgbm(np.ascontiguousarray(l[band]), np.ascontiguousarray(r[band]), **prm)
+    with svgpu.Context(W, 48) as ctx:
+        ctx.set_sgbm(**prm)
+        assert nmismatch(ctx.sgbm(np.ascontiguousarray(l[band]), np.ascontiguousarray(r[band])), want) == 0
+    # full 4K: rectify + SGBM + reproject run end to end; remap and reproject are compared at full size
+    K = np.array([[833.77 * 6, 0, 345.2 * 6], [0, 832.87 * 6, 283.1 * 4.5], [0, 0, 1]])
+    dist = np.array([-0.4168, 0.166, 0, 0, 0])
+    P = np.array([[K[0, 0] * 0.9, 0, K[0, 2], 0], [0, K[0, 0] * 0.9, K[1, 2], 0], [0, 0, 1, 0]])
+    m1, m2 = oracle.init_undistort_rectify_map(K, dist, np.eye(3), P, (W, H))
+    Q = np.array([[1, 0, 0, -K[0, 2]], [0, 1, 0, -K[1, 2]], [0, 0, 0, P[0, 0]], [0, 0, 1 / 75.3, 0]])
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_rectify_maps(0, m1, m2)
+        ctx.set_rectify_maps(1, m1, m2)
+        ctx.set_Q(Q)
+        ctx.set_sgbm(**prm)
+        out = ctx.pipeline(l, r, svgpu.STAGE_REMAP | svgpu.STAGE_SGBM | svgpu.STAGE_REPROJECT, want_rect=True, want_xyz=True)
+        assert nmismatch(out["left_rect"], oracle.remap(l, m1, m2)) == 0
+        xyz = oracle.reproject(out["disp"], Q, True)
+        assert nmismatch(out["xyz"].view(np.uint32), xyz.view(np.uint32)) == 0
+        rows = slice(1200, 1204)
+        assert (out["disp"][rows, D + 100:-100] >= 0).mean() > 0.5
