@@ -54,6 +54,8 @@ struct LaunchStats {
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
                          size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int variant);
+// sgbm_raster.cu: fused raster-sweep aggregation + WTA (schedule 1)
+cudaError_t sgbm_aggregate_raster(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st, LaunchStats* stats);
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
 

@@ -52,11 +52,15 @@ def run(H, W, D, mode, noise=False, variant=-1, **over):
 
 if __name__ == "__main__":
     bad = 0
+    V = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     for mode in (3, 0, 1):
-        bad += run(40, 120, 32, mode)
-        bad += run(33, 100, 16, mode, noise=True, blockSize=3, P1=8, P2=32, uniquenessRatio=0)
-        bad += run(61, 333, 64, mode)
-        bad += run(50, 400, 224, mode)
-        bad += run(37, 150, 48, mode, minDisparity=4)
-        bad += run(37, 150, 48, mode, minDisparity=-8, blockSize=5)
+        bad += run(40, 120, 32, mode, variant=V)
+        bad += run(300, 500, 128, mode, variant=V)
+        bad += run(70, 300, 256, mode, variant=V)
+        bad += run(300, 120, 16, mode, variant=V)
+        bad += run(33, 100, 16, mode, variant=V, noise=True, blockSize=3, P1=8, P2=32, uniquenessRatio=0)
+        bad += run(61, 333, 64, mode, variant=V)
+        bad += run(50, 400, 224, mode, variant=V)
+        bad += run(37, 150, 48, mode, variant=V, minDisparity=4)
+        bad += run(37, 150, 48, mode, variant=V, minDisparity=-8, blockSize=5)
     print("TOTAL BAD", bad)
