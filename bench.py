@@ -145,7 +145,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="svgpu", choices=["svgpu", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("SVGPU_BENCH_BATCH", 8)), help="pairs per step per GPU")
-    ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "svgpu" else args.warmup
@@ -186,7 +185,6 @@ def main():
 
     ctx = svgpu.Context(W, H, device=local)
     ctx.set_sgbm(**SGBM)
-    ctx.set_sgbm_variant(args.variant)
     ctx.reserve(B)
     stream = torch.cuda.Stream(device=dev)  # kernels, copies and the timing events all go on this stream
     torch.cuda.set_stream(stream)
@@ -250,7 +248,6 @@ def main():
         cells = (W - D) * H * D
         # dominant stage: path aggregation. Algorithmic bytes of the whole 8-path chain: 10 B per volume cell
         # (SURVEY.md §8d); of the aggregation stage alone: read C once per sweep, S written once and read once.
-        n_agg_launch = {0: 8}.get(args.variant, 8)
         agg_ms = stage["aggregate"]
         agg_bytes = 8.0 * cells * B  # sweep-1 read C + write S + sweep-2 read C + read S (2 B each)
         roofline = {"bound": "hbm", "kernel": "path aggregation (k_agg_*), all launches of one step",
@@ -265,7 +262,7 @@ def main():
                 "config": {"workload": "1920x1080 pairs, 128 disparities, StereoSGBM MODE_HH + LR check (BASELINE configs[2])",
                            "pairs_per_step_per_gpu": B, "fps": pairs / (ms_max / 1e3), "sharding": f"frame i -> rank i mod {world}",
                            "l2": "per-step working set (cost volumes, ~1 GB per pair) exceeds L2; two input sets alternate",
-                           "variant": args.variant, "checksums": [int(c) for c in stats[:, 3]]},
+                           "checksums": [int(c) for c in stats[:, 3]]},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * W * H), "d2h_bytes_per_step": int(2 * B * W * H),
                         "steps": e2e_steps, "fps": (B * world * e2e_steps) / (ms_e2e_max / 1e3),

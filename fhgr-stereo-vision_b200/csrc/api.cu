@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sgbm_device.cuh"
 
 using namespace svgpu;
 
@@ -25,7 +26,7 @@ struct svgpu_ctx {
   float baseline = 0, focal = 0;
   SgbmCfg cfg{};
   BmCfg bm{};
-  int variant = -1;  // aggregation schedule; -1 = default
+  bool debugS = false;  // test hook: the second sweep also stores the final S volume
 
   int maxBatch = 1;
   // scratch for the SGBM core, sized for (cfg, allocBatch)
@@ -70,7 +71,7 @@ int ensure(svgpu_ctx* c, svgpu_ctx::Buf& b, size_t bytes) {
 void release(svgpu_ctx::Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.n = 0; }
 
 void free_scratch(svgpu_ctx* c) {
-  cudaFree(c->sc.planesL); cudaFree(c->sc.planesR); cudaFree(c->sc.C); cudaFree(c->sc.S); cudaFree(c->sc.wtaKey);
+  cudaFree(c->sc.planesL); cudaFree(c->sc.planesR); cudaFree(c->sc.C); cudaFree(c->sc.S); cudaFree(c->sc.sel);
   cudaFree(c->sc.dispRaw); cudaFree(c->sc.status); cudaFree(c->sc.flags); cudaFree(c->sc.edges);
   c->sc = SgbmScratch{};
   c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0;
@@ -89,7 +90,7 @@ int ensure_scratch(svgpu_ctx* c, int batch) {
   A((void**)&c->sc.planesR, planeBytes);
   A((void**)&c->sc.C, (size_t)batch * cells * 2);
   A((void**)&c->sc.S, (size_t)batch * cells * 2);
-  A((void**)&c->sc.wtaKey, (size_t)batch * g.H * w1 * 4);
+  A((void**)&c->sc.sel, (size_t)batch * g.H * w1 * 8);
   A((void**)&c->sc.dispRaw, (size_t)batch * g.H * g.W * 2);
   A((void**)&c->sc.status, 256);
   A((void**)&c->sc.flags, sgbm_flags_bytes(g, batch));
@@ -157,7 +158,7 @@ int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const
   int rc = ensure_scratch(c, std::max(n, c->maxBatch));
   if (rc) return rc;
   cudaError_t e = sgbm_forward(c->cfg, c->sc, n, dl, ls, lf, dr, rs, rf, dd, ds, df, c->st, &c->stats,
-                               c->timing ? c->ev : nullptr, c->variant);
+                               c->timing ? c->ev : nullptr, c->debugS ? 1 : 0);
   if (e != cudaSuccess) return cuda_fail(c, e, "sgbm_forward");
   if (c->cfg.speckleWindowSize > 0) {  // built-in stage of StereoSGBM::compute (A.7): newVal = INVALID, maxDiff = 16*range
     rc = ensure(c, c->stLabels, (size_t)c->W * c->H * 4);
@@ -291,9 +292,9 @@ SVGPU_API int svgpu_set_sgbm(svgpu_ctx* c, const svgpu_sgbm_params* p) {
   return SV_OK;
 }
 
-SVGPU_API int svgpu_set_sgbm_variant(svgpu_ctx* c, int variant) {
+SVGPU_API int svgpu_debug_keep_volume(svgpu_ctx* c, int on) {
   if (!c) return SV_INVALID_SETTINGS;
-  c->variant = variant;
+  c->debugS = on != 0;
   return SV_OK;
 }
 
@@ -694,9 +695,14 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
 SVGPU_API int svgpu_debug_copy_volume(svgpu_ctx* c, int which, int16_t* host, size_t bytes) {
   SV_STAGE_PROLOGUE();
   if (!host || !c->sc.C) return fail(c, SV_NOT_CONFIGURED, "no volume");
-  const size_t n = std::min(bytes, c->sc.frameCells * 2);
+  const size_t n = std::min(bytes, c->sc.frameCells * 2) / 2;
   CU(c, cudaStreamSynchronize(c->st));
-  CU(c, cudaMemcpy(host, which == 0 ? c->sc.C : c->sc.S, n, cudaMemcpyDeviceToHost));
+  std::vector<int16_t> tmp(n);
+  CU(c, cudaMemcpy(tmp.data(), which == 0 ? c->sc.C : c->sc.S, n * 2, cudaMemcpyDeviceToHost));
+  // undo the interleave inside each group of 16 disparities (sgbm_device.cuh: vol_index)
+  const size_t D = (size_t)c->cfg.D;
+  for (size_t p = 0; p + D <= n; p += D)
+    for (size_t d = 0; d < D; d++) host[p + d] = tmp[p + (size_t)vol_index((int)d)];
   return SV_OK;
 }
 

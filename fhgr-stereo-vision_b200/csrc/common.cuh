@@ -38,7 +38,7 @@ struct SgbmScratch {
   uint8_t* planesR;
   uint16_t* C;        // cost volume Ctrue
   uint16_t* S;        // aggregated volume
-  uint32_t* wtaKey;   // [frame][H][W1]  (minS<<16)|best or 0xFFFFFFFF
+  uint2* sel;         // [frame][H][W1]  winner-take-all result of the second sweep (sgbm_device.cuh)
   int16_t* dispRaw;   // [frame][H][W]   before / after LR check
   int* status;        // device error flag (spin time-outs etc.)
   unsigned long long* flags;  // inter-CTA progress flags of the sweep kernels
@@ -53,9 +53,10 @@ struct LaunchStats {
 // sgbm.cu
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
-                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int variant);
-// sgbm_raster.cu: fused raster-sweep aggregation + WTA (schedule 1)
-cudaError_t sgbm_aggregate_raster(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st, LaunchStats* stats);
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS);
+// sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
+cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
+                                 LaunchStats* stats);
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
 

@@ -8,8 +8,9 @@
 // Data layout in HBM (per pair in flight):
 //   planes  [y][6][Wp] u8      pre-filter rows of one image: g, lo(g), hi(g), i, lo(i), hi(i)
 //   C, S    [y][x'][d] u16     cost volume Ctrue and aggregated costs, d innermost so that one
-//                              pixel's D costs are D*2 contiguous bytes (256 B at D=128)
-//   wtaKey  [y][x']    u32     (minS<<16)|best of pixels that passed uniqueness, else ~0
+//                              pixel's D costs are D*2 contiguous bytes (256 B at D=128); inside each
+//                              group of 16 disparities the halves are interleaved (sgbm_device.cuh)
+//   sel     [y][x']    2 x u32 winner of the pixel: reject<<31 | minS<<16 | best, S[best-1]<<16 | S[best+1]
 // Costs are kept as unsigned 16-bit lanes packed two per register; all min/add work
 // runs on the packed-SIMD integer instructions of sm_100 (VIMNMX.U16x2, VIMNMX3,
 // VIADDMNMX, VIADD.16x2) and __reduce_min_sync (CREDUX).
@@ -201,163 +202,89 @@ __global__ void __launch_bounds__(kCostThreads) k_cost_volume(const uint8_t* __r
     }
     if (prologue) continue;
     __syncthreads();
-    // ---- horizontal window over Vs (clamped in W1 coordinates, A.4) -> Ctrue[y][x'][d0..d0+7]
-    if (live) {
+    // ---- horizontal window over Vs (clamped in W1 coordinates, A.4) -> Ctrue[y][x'][16-group of d]
+    //      two neighbouring lanes hold one group of 16 disparities; they swap halves so that word i of the
+    //      group is (d0+i, d0+i+8) — the interleaved volume layout of sgbm_device.cuh
+    {
       const bool hh4zero = (cfg.mode == SV_MODE_HH4) && (y >= H - r);
-      for (int t = slot; t < kCostTW; t += nslot) {
+      const int trips = (kCostTW + nslot - 1) / nslot;
+      for (int it = 0; it < trips; it++) {
+        const int t = slot + it * nslot;
         const int xp = x0 + t;
-        if (xp >= W1) break;
+        const bool valid = live && t < kCostTW && xp < W1;
         uint4 acc = make_uint4(0, 0, 0, 0);
-        if (!hh4zero) {
+        if (valid && !hh4zero) {
           for (int dx = -r; dx <= r; dx++) {
             const int cc = min(max(xp + dx, 0), W1 - 1) - (x0 - r);
             const uint4 v = *(const uint4*)(sVs + (size_t)cc * D + d0);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
         }
-        *(uint4*)(Cf + ((size_t)y * W1 + xp) * D + d0) = acc;
+        const bool upper = dl & 1;  // this lane holds d0+8..d0+15 of the group
+        const uint32_t s0 = __shfl_xor_sync(0xFFFFFFFFu, upper ? acc.x : acc.z, 1);
+        const uint32_t s1 = __shfl_xor_sync(0xFFFFFFFFu, upper ? acc.y : acc.w, 1);
+        uint4 o;
+        if (!upper) {  // words 0..3: (d, d+8) for d = d0..d0+3
+          o.x = __byte_perm(acc.x, s0, 0x5410); o.y = __byte_perm(acc.x, s0, 0x7632);
+          o.z = __byte_perm(acc.y, s1, 0x5410); o.w = __byte_perm(acc.y, s1, 0x7632);
+        } else {       // words 4..7: (d-8, d) for d = d0..d0+3 of this lane, i.e. group offsets 4..7
+          o.x = __byte_perm(s0, acc.z, 0x5410); o.y = __byte_perm(s0, acc.z, 0x7632);
+          o.z = __byte_perm(s1, acc.w, 0x5410); o.w = __byte_perm(s1, acc.w, 0x7632);
+        }
+        if (valid) *(uint4*)(Cf + ((size_t)y * W1 + xp) * D + d0) = o;
       }
     }
     __syncthreads();
   }
 }
 
-// K3 (variant 0): one group of LPP lanes walks one scan line of one path and accumulates into S.
-// Chains of a diagonal path start on the top/bottom row and on one side column.
-template <int LPP>
-__global__ void __launch_bounds__(128) k_agg_walk(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol,
-                                                  SgbmCfg cfg, int tx, int ty, int accumulate, int nchains,
-                                                  int nframes, size_t frameCells) {
-  const int D = cfg.D, W1 = cfg.W1, H = cfg.H;
-  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPP;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPP;
-  const unsigned gmask = (LPP == 32) ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (lane - gl));
-  const bool active = gl * 8 < D;
-  const int chain = gid % nchains, frame = gid / nchains;
-  int x, y, len = 0;
-  if (frame < nframes) {
-    if (ty == 0) { y = chain; x = tx > 0 ? 0 : W1 - 1; len = W1; }
-    else if (tx == 0) { x = chain; y = ty > 0 ? 0 : H - 1; len = H; }
-    else if (chain < W1) { x = chain; y = ty > 0 ? 0 : H - 1; len = min(H, tx > 0 ? W1 - x : x + 1); }
-    else { const int k = chain - W1; y = ty > 0 ? k + 1 : H - 2 - k; x = tx > 0 ? 0 : W1 - 1; len = min(W1, ty > 0 ? H - y : y + 1); }
-  } else { x = y = 0; }
-  // warp-uniform trip count so that the full-mask shuffles stay converged
-  int maxlen = len;
-#pragma unroll
-  for (int o = 16; o >= LPP && o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xFFFFFFFFu, maxlen, o));
-  if (LPP == 32) maxlen = len;
-
-  const long long stepEl = ((long long)ty * W1 + tx) * D;
-  const uint16_t* cp = Cvol + (size_t)frame * (frame < nframes ? frameCells : 0) + ((size_t)y * W1 + x) * D + gl * 8;
-  uint16_t* sp = Svol + (size_t)frame * (frame < nframes ? frameCells : 0) + ((size_t)y * W1 + x) * D + gl * 8;
-  const uint32_t p1dup = dup16(cfg.P1), p2dup = dup16(cfg.P2);
-
-  uint32_t L[4] = {kMax2, kMax2, kMax2, kMax2}, mdup = 0;
-  uint4 cnext = make_uint4(0, 0, 0, 0), snext = make_uint4(0, 0, 0, 0);
-  if (active && len > 0) {
-    cnext = *(const uint4*)cp;
-    if (accumulate) snext = *(const uint4*)sp;
-  }
-  for (int i = 0; i < maxlen; i++) {
-    const bool on = i < len;
-    const uint4 c = cnext, s = snext;
-    if (active && i + 1 < len) {
-      cnext = *(const uint4*)(cp + stepEl);
-      if (accumulate) snext = *(const uint4*)(sp + stepEl);
-    }
-    if (i == 0) sgm_first(L, mdup, c, gmask, active && on);
-    else sgm_step<LPP>(L, mdup, c, p1dup, p2dup, gmask, gl, active && on);
-    if (active && on) {
-      uint4 o;
-      if (accumulate) {
-        o.x = __viaddmin_u16x2(s.x, L[0], kMax2); o.y = __viaddmin_u16x2(s.y, L[1], kMax2);
-        o.z = __viaddmin_u16x2(s.z, L[2], kMax2); o.w = __viaddmin_u16x2(s.w, L[3], kMax2);
-      } else { o.x = L[0]; o.y = L[1]; o.z = L[2]; o.w = L[3]; }
-      *(uint4*)sp = o;
-    }
-    cp += stepEl; sp += stepEl;
-  }
-}
-
-template <int LPP>
-__global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, uint32_t* __restrict__ wtaKey,
-                                             int16_t* __restrict__ dispRaw, SgbmCfg cfg, int nframes, size_t frameCells) {
-  const int lane = threadIdx.x & 31, gl = lane % LPP;
-  const unsigned gmask = (LPP == 32) ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (lane - gl));
-  const bool active = gl * 8 < cfg.D;
-  const long long npix = (long long)nframes * cfg.H * cfg.W1;
-  const long long groupsPerGrid = (long long)gridDim.x * blockDim.x / LPP;
-  long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
-  // warp-uniform loop: every group of the warp iterates the same number of times
-  const long long warpFirst = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LPP;
-  for (long long base = warpFirst; base < npix; base += groupsPerGrid, pix += groupsPerGrid) {
-    const bool on = pix < npix;
-    uint32_t s[4] = {kMax2, kMax2, kMax2, kMax2};
-    int frame = 0, y = 0, xp = 0;
-    if (on) {
-      frame = (int)(pix / ((long long)cfg.H * cfg.W1));
-      const long long rem = pix % ((long long)cfg.H * cfg.W1);
-      y = (int)(rem / cfg.W1); xp = (int)(rem % cfg.W1);
-      if (active) {
-        const uint4 v = *(const uint4*)(Svol + (size_t)frame * frameCells + ((size_t)y * cfg.W1 + xp) * cfg.D + gl * 8);
-        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-      }
-    }
-    int dsp; uint32_t key;
-    wta_pixel<LPP>(s, gl, gmask, active && on, cfg, dsp, key);
-    if (on && gl == 0) {
-      wtaKey[((size_t)frame * cfg.H + y) * cfg.W1 + xp] = key;
-      dispRaw[((size_t)frame * cfg.H + y) * cfg.W + xp + cfg.minX1] = (int16_t)dsp;
-    }
-  }
-}
-
-// K5: left-right consistency check of one image row (A.6, second half).  disp2 is rebuilt by a
-// scatter-min of (minS, W1-1-x') keys: lowest cost wins, ties go to the largest x' — the same
-// winner as OpenCV's right-to-left scan with a strict '>' test.
-__global__ void __launch_bounds__(256) k_lr_check(const uint32_t* __restrict__ wtaKey, int16_t* __restrict__ dispRaw, SgbmCfg cfg) {
-  extern __shared__ uint32_t sKey[];  // [W]
+// K5: sub-pixel disparity + left-right consistency check of one image row (A.6, second half), from the
+// per-pixel selection the second sweep left in `sel`.  disp2 is rebuilt by a scatter-min of
+// (minS, W1-1-x') keys: lowest cost wins, ties go to the largest x' — the same winner as OpenCV's
+// right-to-left scan with a strict '>' test.
+__global__ void __launch_bounds__(256) k_select_lr(const uint2* __restrict__ sel, int16_t* __restrict__ dispRaw, SgbmCfg cfg) {
+  extern __shared__ uint32_t sKey[];  // [W] keys, then [W] int16 disparities
   const int y = blockIdx.x, frame = blockIdx.y;
   const int W = cfg.W, W1 = cfg.W1;
-  const uint32_t* keys = wtaKey + ((size_t)frame * cfg.H + y) * W1;
+  int16_t* sDisp = (int16_t*)(sKey + W);
+  const uint2* row = sel + ((size_t)frame * cfg.H + y) * W1;
   int16_t* dr = dispRaw + ((size_t)frame * cfg.H + y) * W;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) sKey[x] = 0xFFFFFFFFu;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) { sKey[x] = 0xFFFFFFFFu; sDisp[x] = (int16_t)cfg.invalid; }
   __syncthreads();
   for (int xp = threadIdx.x; xp < W1; xp += blockDim.x) {
-    const uint32_t k = keys[xp];
-    if (k == 0xFFFFFFFFu) continue;
-    const int best = (int)(k & 0xFFFFu);
+    const uint2 v = row[xp];
+    const int minS = (int)((v.x >> 16) & 0x7FFFu), best = (int)(v.x & 0xFFFFu);
+    if ((v.x & 0x80000000u) || minS >= 32767) continue;  // not unique / all costs saturated
     const int x2 = xp + cfg.minX1 - best - cfg.minD;
-    atomicMin(&sKey[x2], (k & 0xFFFF0000u) | (uint32_t)(W1 - 1 - xp));
+    atomicMin(&sKey[x2], ((uint32_t)minS << 16) | (uint32_t)(W1 - 1 - xp));
+    int dfix = best * 16;
+    if (best > 0 && best < cfg.D - 1) {
+      const int vm = (int)(v.y >> 16), vp = (int)(v.y & 0xFFFFu);
+      const int den = max(vm + vp - 2 * minS, 1);
+      dfix += ((vm - vp) * 16 + den) / (den * 2);
+    }
+    sDisp[xp + cfg.minX1] = (int16_t)(dfix + cfg.minD * 16);
   }
   __syncthreads();
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    if (x < cfg.minX1 || x >= cfg.minX1 + W1) { dr[x] = (int16_t)cfg.invalid; continue; }
-    const int d1 = dr[x];
-    if (d1 == cfg.invalid) continue;
-    const int _d = d1 >> 4, d_ = (d1 + 15) >> 4, _x = x - _d, x_ = x - d_;
-    bool bad = true;
-    {
-      bool c = false;
+    int d1 = sDisp[x];
+    if (x >= cfg.minX1 && x < cfg.minX1 + W1 && d1 != cfg.invalid) {
+      const int _d = d1 >> 4, d_ = (d1 + 15) >> 4, _x = x - _d, x_ = x - d_;
+      bool c0 = false, c1 = false;
       if (_x >= 0 && _x < W) {
         const uint32_t k = sKey[_x];
         // disp2 holds best+minD of the winner, or (minD-1)*16 when nothing landed there
         const int d2 = (k == 0xFFFFFFFFu) ? cfg.invalid : ((W1 - 1 - (int)(k & 0xFFFFu)) + cfg.minX1 - _x);
-        c = d2 >= cfg.minD && abs(d2 - _d) > cfg.d12;
+        c0 = d2 >= cfg.minD && abs(d2 - _d) > cfg.d12;
       }
-      bad = bad && c;
-    }
-    {
-      bool c = false;
       if (x_ >= 0 && x_ < W) {
         const uint32_t k = sKey[x_];
         const int d2 = (k == 0xFFFFFFFFu) ? cfg.invalid : ((W1 - 1 - (int)(k & 0xFFFFu)) + cfg.minX1 - x_);
-        c = d2 >= cfg.minD && abs(d2 - d_) > cfg.d12;
+        c1 = d2 >= cfg.minD && abs(d2 - d_) > cfg.d12;
       }
-      bad = bad && c;
+      if (c0 && c1) d1 = cfg.invalid;
     }
-    if (bad) dr[x] = (int16_t)cfg.invalid;
+    dr[x] = (int16_t)d1;
   }
 }
 
@@ -373,39 +300,12 @@ __global__ void k_fill_rows_s16(int16_t* p, size_t stride, size_t frame, int W, 
 // host side
 // ------------------------------------------------------------------------------------------------
 
-template <typename F>
-static void with_lpp(int D, F&& f) {
-  const int v = D / 8;
-  if (v <= 2) f(std::integral_constant<int, 2>());
-  else if (v <= 4) f(std::integral_constant<int, 4>());
-  else if (v <= 8) f(std::integral_constant<int, 8>());
-  else if (v <= 16) f(std::integral_constant<int, 16>());
-  else f(std::integral_constant<int, 32>());
-}
-
 #define SV_RET(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
 #define SV_LAUNCHED() do { if (stats) stats->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
-static cudaError_t launch_walk(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int tx, int ty, int accumulate,
-                               cudaStream_t st, LaunchStats* stats) {
-  const int nchains = ty == 0 ? cfg.H : (tx == 0 ? cfg.W1 : cfg.W1 + cfg.H - 1);
-  cudaError_t err = cudaSuccess;
-  with_lpp(cfg.D, [&](auto lpp) {
-    constexpr int LPP = decltype(lpp)::value;
-    const long long threads = (long long)nchains * nframes * LPP;
-    const int block = 128;
-    const int grid = (int)((threads + block - 1) / block);
-    k_agg_walk<LPP><<<grid, block, 0, st>>>(sc.C, sc.S, cfg, tx, ty, accumulate, nchains, nframes, sc.frameCells);
-    err = cudaGetLastError();
-  });
-  if (stats) stats->launches++;
-  return err;
-}
-
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
-                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int variant) {
-  (void)variant;
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS) {
   const int W = cfg.W, H = cfg.H;
   if (cfg.W1 <= 0) {  // A.1: nothing computable, whole map invalid
     dim3 g((W + 255) / 256, H, nframes);
@@ -438,35 +338,11 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
     SV_LAUNCHED();
   }
   if (ev) SV_RET(cudaEventRecord(ev[1], st));
-  const bool raster = variant != 0;  // schedule 1 (fused raster sweeps) is the default; 0 = one kernel per direction
-  if (raster) {
-    SV_RET(sgbm_aggregate_raster(cfg, sc, nframes, st, stats));
-    if (ev) SV_RET(cudaEventRecord(ev[2], st));
-  } else {
-    // predecessor offsets of A.5, expressed as travel directions (tx,ty) = -offset
-    static const int sgbm5[5][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}};
-    static const int hh8[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
-    static const int hh4[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
-    const int(*dirs)[2] = cfg.mode == SV_MODE_SGBM ? sgbm5 : (cfg.mode == SV_MODE_HH ? hh8 : hh4);
-    const int nd = cfg.mode == SV_MODE_SGBM ? 5 : (cfg.mode == SV_MODE_HH ? 8 : 4);
-    for (int i = 0; i < nd; i++) SV_RET(launch_walk(cfg, sc, nframes, dirs[i][0], dirs[i][1], i > 0, st, stats));
-    if (ev) SV_RET(cudaEventRecord(ev[2], st));
-    cudaError_t err = cudaSuccess;
-    with_lpp(cfg.D, [&](auto lpp) {
-      constexpr int LPP = decltype(lpp)::value;
-      const long long npix = (long long)nframes * H * cfg.W1;
-      const int block = 256;
-      const long long want = (npix * LPP + block - 1) / block;
-      const int grid = (int)std::min<long long>(want, 148LL * 8 * 4);
-      k_wta<LPP><<<grid, block, 0, st>>>(sc.S, sc.wtaKey, sc.dispRaw, cfg, nframes, sc.frameCells);
-      err = cudaGetLastError();
-    });
-    if (stats) stats->launches++;
-    SV_RET(err);
-  }
+  SV_RET(sgbm_aggregate_sweep(cfg, sc, nframes, debugS, st, stats));
+  if (ev) SV_RET(cudaEventRecord(ev[2], st));
   {
     dim3 g(H, nframes);
-    k_lr_check<<<g, 256, (size_t)W * sizeof(uint32_t), st>>>(sc.wtaKey, sc.dispRaw, cfg);
+    k_select_lr<<<g, 256, (size_t)W * 6, st>>>(sc.sel, sc.dispRaw, cfg);
     SV_LAUNCHED();
     SV_RET(launch_median3(sc.dispRaw, (size_t)W * 2, disp, dstride, W, H, nframes, (size_t)W * H * 2, dframe, st));
     if (stats) stats->launches++;

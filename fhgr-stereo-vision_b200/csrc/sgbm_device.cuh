@@ -1,113 +1,160 @@
-// sgbm_device.cuh — device building blocks shared by the SGBM aggregation kernels (sgbm.cu, sgbm_raster.cu):
-// one min-plus path step on packed 16-bit costs, and the per-pixel winner-take-all / uniqueness / sub-pixel
-// selection.  Arithmetic: SURVEY.md Appendix A.5 / A.6 (cv::StereoSGBM::compute, src/lib.cpp:262).
+// sgbm_device.cuh — device building blocks of the SGBM aggregation sweep (sgbm_sweep.cu): one min-plus path
+// step on packed 16-bit costs and the per-pixel winner-take-all / uniqueness selection.
+// Arithmetic: SURVEY.md Appendix A.5 / A.6 (cv::StereoSGBM::compute, /root/reference/src/lib.cpp:262).
+//
+// Register layout of one pixel's costs: a worker is a group of LPP lanes, lane gl holds the 16 disparities
+// d0 = 16*gl .. d0+15 in kNR = 8 packed registers, register i = (d0+i) | (d0+i+8) << 16.  With that
+// interleave the d-1 / d+1 neighbours of register i are registers i-1 / i+1 of the same lane; only
+// register 0 and register 7 need one value from the neighbouring lane.
 #pragma once
 #include "common.cuh"
 
 namespace svgpu {
 
 static constexpr uint32_t kMax2 = 0x7FFF7FFFu;  // two lanes of MAX_COST (32767)
+static constexpr int kDPL = 16;                 // disparities per lane
+static constexpr int kNR = kDPL / 2;            // packed registers per lane and path
 
-__device__ __forceinline__ uint32_t dup16(uint32_t v) { return v | (v << 16); }
-__device__ __forceinline__ uint32_t hmin16(uint32_t v) { return min(v & 0xFFFFu, v >> 16); }
+__host__ __device__ __forceinline__ uint32_t dup16(uint32_t v) { return v | (v << 16); }
 
-// ------------------------------------------------------------------------------------------------
-// Path aggregation (A.5).  One min-plus step of one path for 8 disparities per lane.
-//   L      previous / next path costs of this lane (4 packed registers, u16x2)
-//   mdup   min over all d of the previous L, duplicated in both halves
-//   c      Ctrue of the current pixel
-// Neighbouring lanes exchange their border disparities with two shuffles; lanes beyond D hold
-// MAX_COST so that they act as the L(q,-1) = L(q,D) = 32767 boundary.
-// ------------------------------------------------------------------------------------------------
+// position of disparity d inside its pixel's D costs in volume memory (uint16 index)
+__host__ __device__ __forceinline__ int vol_index(int d) { return (d & ~15) | ((d & 7) << 1) | ((d >> 3) & 1); }
+
+struct SweepK {
+  uint32_t p1dup;     // P1 | P1<<16
+  uint32_t p2mp1dup;  // (P2-P1) twice
+  uint32_t negp1dup;  // (-P1 mod 2^16) twice
+};
+
+// min / sum over the LPP lanes of a worker; every lane of the warp must call
 template <int LPP>
-__device__ __forceinline__ void sgm_step(uint32_t (&L)[4], uint32_t& mdup, const uint4& c, uint32_t p1dup,
-                                         uint32_t p2dup, unsigned gmask, int gl, bool active) {
-  uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[3], 1, LPP);
-  uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPP);
-  if (gl == 0) up = kMax2;
-  if (gl == LPP - 1) dn = kMax2;
-  const uint32_t mp2 = mdup + p2dup;
-  const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-  uint32_t prev = up, n[4];
+__device__ __forceinline__ uint32_t group_min_u32(uint32_t v, int lane) {
+  if constexpr (LPP == 1) return v;
+  else if constexpr (LPP == 32) return __reduce_min_sync(0xFFFFFFFFu, v);
+  else if constexpr (LPP == 16) {  // two full-warp CREDUX beat a four-step shuffle butterfly
+    const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, lane < 16 ? v : 0xFFFFFFFFu);
+    const uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, lane < 16 ? 0xFFFFFFFFu : v);
+    return lane < 16 ? lo : hi;
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t next = (i < 3) ? L[i + 1] : dn;
-    const uint32_t lm1 = __byte_perm(prev, L[i], 0x5432);  // L(q,d-1) for the pair
-    const uint32_t lp1 = __byte_perm(L[i], next, 0x5432);  // L(q,d+1)
-    uint32_t t = __viaddmin_u16x2(__vminu2(lm1, lp1), p1dup, mp2);
-    t = __vminu2(t, L[i]);
-    n[i] = __vadd2(t, __vsub2(cc[i], mdup));
-    prev = L[i];
+    for (int o = LPP / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
   }
-  uint32_t mn = __vminu2(__vminu2(n[0], n[1]), __vminu2(n[2], n[3]));
-#pragma unroll
-  for (int i = 0; i < 4; i++) L[i] = active ? n[i] : kMax2;
-  uint32_t m = active ? hmin16(mn) : 0x7FFFu;
-  m = __reduce_min_sync(gmask, m);
-  mdup = dup16(m);
 }
-
-// first pixel of a path: predecessor outside the volume, L = Ctrue
-__device__ __forceinline__ void sgm_first(uint32_t (&L)[4], uint32_t& mdup, const uint4& c, unsigned gmask, bool active) {
-  L[0] = active ? c.x : kMax2; L[1] = active ? c.y : kMax2; L[2] = active ? c.z : kMax2; L[3] = active ? c.w : kMax2;
-  uint32_t m = hmin16(__vminu2(__vminu2(L[0], L[1]), __vminu2(L[2], L[3])));
-  m = __reduce_min_sync(gmask, m);
-  mdup = dup16(m);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4: winner-take-all + uniqueness + sub-pixel (A.6, first half) for one pixel held by a lane group
-//   s = final S of the pixel (this lane's 8 disparities).  Returns the raw CV_16S value (or invalid)
-//   and the key (minS<<16)|best (or ~0) that feeds the left-right check.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pick16(const uint32_t (&s)[4], int e) {  // element e (0..7) of the lane
-  const uint32_t w = (e & 4) ? ((e & 2) ? s[3] : s[2]) : ((e & 2) ? s[1] : s[0]);
-  return (e & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
-
 template <int LPP>
-__device__ __forceinline__ void wta_pixel(const uint32_t (&s)[4], int gl, unsigned gmask, bool active,
-                                          const SgbmCfg& cfg, int& dispOut, uint32_t& keyOut) {
-  const int d0 = gl * 8;
+__device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, int lane) {
+  if constexpr (LPP == 1) return v;
+  else if constexpr (LPP == 32) return __reduce_add_sync(0xFFFFFFFFu, v);
+  else if constexpr (LPP == 16) {
+    const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, lane < 16 ? v : 0u);
+    const uint32_t hi = __reduce_add_sync(0xFFFFFFFFu, lane < 16 ? 0u : v);
+    return lane < 16 ? lo : hi;
+  } else {
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Path aggregation (A.5): one step of one path for the 16 disparities of this lane.
+//   L      in: path costs of the predecessor pixel, out: path costs of this pixel
+//   mdup   in: min_d L(predecessor) in both halves, out: the same for this pixel
+//   outside  the predecessor lies outside the volume (L = 0, min = 0): the result is Ctrue.  This is
+//          expressed through the two scalars only, so L may then hold any values in [0, 32767]
+//   c      Ctrue of this pixel
+// L(p,d) = C + min(L(q,d), L(q,d-1)+P1, L(q,d+1)+P1, m+P2) - m, evaluated as
+//   x = min3_s16(L(d-1), L(d+1), m+P2-P1);  y = min_u16(x+P1, L(d));  L' = y + C - m
+// (3 instructions per packed register; no half ever borrows or carries because m <= y and y + C < 2^16).
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& mdup, bool outside, const uint32_t (&c)[kNR],
+                                                const SweepK& k, int gl, int lastLane, bool active, int lane) {
+  uint32_t up = kMax2, dn = kMax2;
+  if (LPP > 1) {
+    up = __shfl_up_sync(0xFFFFFFFFu, L[kNR - 1], 1, LPP);
+    dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPP);
+    if (gl == 0) up = kMax2;         // L(q,-1) = MAX_COST
+    if (gl == lastLane) dn = kMax2;  // L(q,D)  = MAX_COST
+  }
+  const uint32_t capm = outside ? k.negp1dup : mdup + k.p2mp1dup;
+  const uint32_t msub = outside ? 0u : mdup;
+  const uint32_t lm0 = __byte_perm(up, L[kNR - 1], 0x5432);  // (d0-1, d0+7)
+  const uint32_t lpN = __byte_perm(L[0], dn, 0x5432);        // (d0+8, d0+16)
+  uint32_t n[kNR];
+#pragma unroll
+  for (int i = 0; i < kNR; i++) {
+    const uint32_t lm = i ? L[i - 1] : lm0, lp = (i < kNR - 1) ? L[i + 1] : lpN;
+    const uint32_t x = __vimin3_s16x2(lm, lp, capm);
+    const uint32_t y = __viaddmin_u16x2(x, k.p1dup, L[i]);
+    n[i] = y + c[i] - msub;
+  }
+  uint32_t mn = __vimin3_u16x2(n[0], n[1], n[2]);
+  mn = __vimin3_u16x2(mn, n[3], n[4]);
+  mn = __vimin3_u16x2(mn, n[5], n[6]);
+  mn = __vminu2(mn, n[7]);
+  mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
+  if (!active) mn = 0xFFFFFFFFu;
+  mdup = group_min_u32<LPP>(mn, lane);
+#pragma unroll
+  for (int i = 0; i < kNR; i++) L[i] = n[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Winner-take-all + uniqueness of one pixel (A.6, first half), run by the worker that holds its final S.
+//   out.x = reject << 31 | minS << 16 | best        out.y = S[best-1] << 16 | S[best+1]
+// Uniqueness ("some d with S[d]*(100-uniq) < minS*100 and |d-best| > 1") is decided without a per-cell
+// compare: with thr = ceil(minS*100 / (100-uniq)) a cell qualifies iff S[d] < thr; the summed shortfall
+// sum_d max(thr - S[d], 0) exceeds the shortfall of {best-1, best, best+1} iff another cell qualifies.
+// `scratch` holds the pixel's S so that the two neighbours of the winner can be looked up by index.
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __forceinline__ void sweep_wta(const uint32_t (&s)[kNR], uint16_t* scratch, int gl, bool active, int lane, int D,
+                                          int uniqF, uint32_t uniqMagic, uint2& out) {
+  const int d0 = gl * kDPL;
   uint32_t k = 0xFFFFFFFFu;
   if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      k = min(k, (s[i] << 16) | (uint32_t)(d0 + 2 * i));
-      k = min(k, (s[i] & 0xFFFF0000u) | (uint32_t)(d0 + 2 * i + 1));
+    for (int i = 0; i < kNR; i += 2) {
+      const uint32_t a = s[i] * 65536u + (uint32_t)(d0 + i), b = (s[i] & 0xFFFF0000u) | (uint32_t)(d0 + i + 8);
+      const uint32_t e = s[i + 1] * 65536u + (uint32_t)(d0 + i + 1), f = (s[i + 1] & 0xFFFF0000u) | (uint32_t)(d0 + i + 9);
+      k = __vimin3_u32(k, a, b);
+      k = __vimin3_u32(k, e, f);
     }
   }
-  k = __reduce_min_sync(gmask, k);
+  k = group_min_u32<LPP>(k, lane);
   const int minS = (int)(k >> 16), best = (int)(k & 0xFFFFu);
-  dispOut = cfg.invalid;
-  keyOut = 0xFFFFFFFFu;
-  // neighbours of the winner for the parabola (owners publish, everybody reduces)
-  const int e1 = best - 1, e2 = best + 1;
-  uint32_t vm = 0, vp = 0;
-  if (active && e1 >= d0 && e1 < d0 + 8) vm = pick16(s, e1 - d0);
-  if (active && e2 >= d0 && e2 < d0 + 8) vp = pick16(s, e2 - d0);
-  vm = __reduce_max_sync(gmask, vm);
-  vp = __reduce_max_sync(gmask, vp);
-  // uniqueness: any d with S[d]*(100-uniq) < minS*100 and |best-d| > 1 rejects the pixel
-  bool rej = false;
+  // publish S of the pixel, look up the neighbours of the winner
+  __syncwarp();
   if (active) {
-    const int f = 100 - cfg.uniq, t = minS * 100;
+    uint4* sp = (uint4*)scratch + gl * 2;
+    sp[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    sp[1] = make_uint4(s[4], s[5], s[6], s[7]);
+  }
+  __syncwarp();
+  const int vm = best > 0 ? (int)scratch[vol_index(best - 1)] : 0;
+  const int vp = best < D - 1 ? (int)scratch[vol_index(best + 1)] : 0;
+  // shortfall against thr
+  uint32_t thr;
+  {
+    const uint32_t num = (uint32_t)minS * 100u + (uint32_t)uniqF - 1u;
+    const uint32_t q = uniqF >= 2 ? __umulhi(num, uniqMagic) : (uniqF == 1 ? num : (minS ? 32768u : 0u));
+    thr = min(q, 32768u);
+  }
+  const uint32_t thrdup = dup16(thr);
+  uint32_t acc = 0;
+  if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int a = (int)(s[i] & 0xFFFFu), b = (int)(s[i] >> 16), da = d0 + 2 * i;
-      rej |= (a * f < t) && (abs(best - da) > 1);
-      rej |= (b * f < t) && (abs(best - da - 1) > 1);
-    }
+    for (int i = 0; i < kNR; i++) acc = __dp2a_lo(__vminu2(s[i], thrdup), 0x0101u, acc);
   }
-  const unsigned rejBallot = __ballot_sync(0xFFFFFFFFu, rej) & gmask;
-  if (minS >= 32767 || rejBallot) return;
-  int dfix = best * 16;
-  if (best > 0 && best < cfg.D - 1) {
-    const int den = max((int)vm + (int)vp - 2 * minS, 1);
-    dfix += (((int)vm - (int)vp) * 16 + den) / (den * 2);
-  }
-  dispOut = dfix + cfg.minD * 16;
-  keyOut = k;
+  acc = group_sum_u32<LPP>(acc, lane);
+  const int total = D * (int)thr - (int)acc;
+  int allowed = (int)thr - minS;
+  if (best > 0) allowed += max((int)thr - vm, 0);
+  if (best < D - 1) allowed += max((int)thr - vp, 0);
+  const uint32_t rej = total > allowed ? 0x80000000u : 0u;
+  out.x = k | rej;
+  out.y = ((uint32_t)vm << 16) | (uint32_t)vp;
 }
 
 }  // namespace svgpu

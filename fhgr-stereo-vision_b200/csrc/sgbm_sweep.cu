@@ -1,0 +1,528 @@
+// sgbm_sweep.cu — SGM path aggregation as two fused sweeps over skewed column strips.
+//
+// Replaces the aggregation + winner-take-all inside cv::StereoSGBM::compute
+// (/root/reference/src/lib.cpp:262; arithmetic: SURVEY.md A.5 / A.6).
+//
+// A raster-order sweep can carry the four paths whose predecessor lies to the left or in the row above
+// (travel directions ->, down-right, down, down-left); the reverse sweep carries the other four.  MODE_HH
+// therefore needs two passes over the cost volume: pass 1 reads C and writes S = sum of 4 paths, pass 2
+// reads C and S, adds its 4 paths and selects the winner in registers: 8 B per volume cell in total.
+//
+// Work decomposition (per pass, in sweep coordinates; pass 2 is pass 1 on the volume flipped in x and y):
+//   * the image is cut into strips of kK columns whose borders move one pixel to the left per row:
+//     strip s covers columns [s*kK - y, s*kK - y + kK) of row y.  With that skew every predecessor of a
+//     pixel — (x-1,y), (x-1,y-1), (x,y-1), (x+1,y-1) — lies in the same strip or in the strip to the LEFT,
+//     so strips form a one-directional pipeline;
+//   * a "worker" is a group of LPP lanes (16 disparities per lane) that owns one strip and walks it top to
+//     bottom, kK pixels per row ("chunk").  The horizontal path lives in registers; the three paths that
+//     come from the row above live in a lane-private shared-memory row buffer (kK records);
+//   * per chunk a worker receives from its left neighbour the horizontal path of the pixel left of the
+//     chunk and the vertical/diagonal paths of the two pixels above-left of it, and hands the same to its
+//     right neighbour: one small "entry" per row instead of one hand-over per pixel;
+//   * a warp holds 32/LPP neighbouring strips in lock step, one row apart (entries through shared memory,
+//     __syncwarp only); warps of a CTA hand over through shared-memory rings with acquire/release
+//     counters; CTAs hand over through a global edge buffer + progress counter;
+//   * CTAs are persistent and draw (frame, strip group) tasks from a ticket counter, strip groups in
+//     ascending order.  A task only waits for the task to its left, which has a smaller ticket and is
+//     therefore resident or finished: no deadlock whatever the residency.
+//
+// Volume layout: [frame][y][x'][D] uint16, the D costs of a pixel in groups of 16 with the two halves of a
+// group interleaved (word i of a group = disparities d0+i and d0+i+8), so that the d-1 / d+1 neighbours of
+// a packed register are simply the previous / next register of the lane (sgbm_device.cuh).
+#include <algorithm>
+
+#include "common.cuh"
+#include "sgbm_device.cuh"
+
+namespace svgpu {
+
+namespace {
+
+constexpr int kK = 4;          // strip width = pixels per chunk
+constexpr int kRingX = 4;      // entries in the import ring of a warp's first worker (fed by another warp / CTA)
+constexpr int kRingI = 2;      // entries in the import ring of the other workers (fed in lock step by the same warp)
+constexpr int kSpinLimit = 1 << 24;
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kMaxNW = 8;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
+
+enum : int { P_H = 1, P_DL = 2, P_V = 4, P_DR = 8 };
+
+template <int LPP, bool SECOND>
+struct SweepGeom {
+  static constexpr int RW = 32 / LPP;             // workers (strips) per warp
+  static constexpr int NV = kNR / 4;              // uint4 per lane per path vector
+  static constexpr int VEC = LPP * NV;            // uint4 per path vector of one pixel
+  static constexpr int REC = 3 * VEC;             // record of one pixel: V, DL, DR
+  static constexpr int ENT = 4 * VEC + 1;         // hand-over entry of one row: H, V1, DL1, DL0, mins
+  static constexpr int ROWBUF = kK * REC;         // per worker
+  static constexpr int WTA = SECOND ? VEC : 0;    // per worker: final S of one pixel (neighbour lookup)
+  static constexpr int OFF_RING = RW * ROWBUF;    // in-warp rings of workers 1..RW-1, then the ring of worker 0
+  static constexpr int OFF_RING0 = OFF_RING + (RW - 1) * kRingI * ENT;
+  static constexpr int OFF_WTA = OFF_RING0 + kRingX * ENT;
+  static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
+  static constexpr int NW_FIT = (kSmemMax - 256) / (WARP_U4 * 16);
+  static constexpr int NW = NW_FIT > kMaxNW ? kMaxNW : NW_FIT;  // warps per CTA
+  static constexpr int SPC = NW * RW;             // strips per CTA task
+  static constexpr size_t SMEM = (size_t)NW * WARP_U4 * 16 + 256;
+};
+
+struct SweepArgs {
+  const uint4* C;
+  uint4* S;
+  uint2* sel;     // [frame][H][W1]  pass 2: {reject<<31 | minS<<16 | best, S[best-1]<<16 | S[best+1]}
+  uint4* edges;   // [frame][G-1][H][ENT]
+  int* gprog;     // [frame][G]  rows of the strip group's last strip that are visible in `edges`
+  int* ticket;
+  int* status;
+  int W1, H, D, nAct;          // nAct = D/16 lanes of a worker hold disparities
+  int nframes, G, smax, flip, debugS;
+  unsigned frameU4;            // uint4 per frame of a volume
+  unsigned rowU4;              // uint4 per volume row = W1*D/8
+  int pixU4;                   // uint4 per pixel = D/8
+  uint32_t p1dup, p2mp1dup, negp1dup;
+  int uniqF;                   // 100 - uniquenessRatio
+  uint32_t uniqMagic;          // ceil(2^32 / uniqF) for uniqF >= 2
+};
+
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint4* smemDst, const uint4* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// spin until *flag >= need; false when the kernel is being aborted
+__device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int* sAbort, int* status) {
+  int n = 0;
+  while (ld_acquire_cta(flag) < need) {
+    if (((++n) & 1023) == 0) {
+      if (*sAbort) return false;
+      if (n > kSpinLimit) { *sAbort = 1; atomicExch(status, 1); return false; }
+    }
+  }
+  return true;
+}
+
+template <int LPP, int PATHS, bool SECOND>
+__global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(const SweepArgs a) {
+  using G = SweepGeom<LPP, SECOND>;
+  constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
+  constexpr bool HAS_V = (PATHS & P_V) != 0, HAS_DL = (PATHS & P_DL) != 0, HAS_DR = (PATHS & P_DR) != 0;
+  constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
+  extern __shared__ uint4 smem[];
+  int* flags = (int*)(smem + NW * G::WARP_U4);
+  int* sProg = flags;            // [NW] rows exported by the last worker of warp w
+  int* sCons = flags + NW;       // [NW] rows finished by the first worker of warp w
+  int* sTicket = flags + 2 * NW;
+  volatile int* sAbort = flags + 2 * NW + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane / LPP, gl = lane % LPP;
+  const int W1 = a.W1, H = a.H;
+  const bool active = gl < a.nAct;           // lane holds disparities
+  const int lastLane = a.nAct - 1;
+  SweepK kc;
+  kc.p1dup = a.p1dup; kc.p2mp1dup = a.p2mp1dup; kc.negp1dup = a.negp1dup;
+
+  // shared memory starts out as valid (zero) path costs: stale entries are read under an override only
+  for (int i = threadIdx.x; i < NW * G::WARP_U4; i += blockDim.x) smem[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) *sAbort = 0;
+
+  uint4* wbase = smem + warp * G::WARP_U4;
+  uint4* rowbuf = wbase + j * G::ROWBUF + gl;  // lane-private: [pixel][path][half][gl]
+  uint4* inRing = wbase + (j > 0 ? G::OFF_RING + (j - 1) * kRingI * ENT : G::OFF_RING0);
+  const int inMask = j > 0 ? kRingI - 1 : kRingX - 1;
+  uint4* outRing = (j < RW - 1) ? wbase + G::OFF_RING + j * kRingI * ENT : wbase + G::WARP_U4 + G::OFF_RING0;
+  const int outMask = (j < RW - 1) ? kRingI - 1 : kRingX - 1;
+  uint4* ring0 = wbase + G::OFF_RING0;
+  uint16_t* wta = (uint16_t*)(wbase + G::OFF_WTA + j * G::WTA);
+
+  const int ntasks = a.nframes * a.G;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *sTicket = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int task = *sTicket;
+    if (task >= ntasks || *sAbort) break;
+    const int frame = task % a.nframes, sg = task / a.nframes;
+    const int sFirst = sg * G::SPC + warp * RW;  // strip of this warp's worker 0
+    auto y0of = [&](int s) { return max(0, s * kK - W1 + 1); };
+    auto y1of = [&](int s) { return min(H - 1, s * kK + kK - 1); };
+    if (lane == 0) { sProg[warp] = 0; sCons[warp] = y0of(sFirst); }
+    __syncthreads();
+    if (sFirst > a.smax) continue;  // whole warp beyond the last strip (still takes part in the barriers above)
+
+    const int s = sFirst + j;
+    const int y0 = y0of(s), y1 = y1of(s);            // rows of this strip (empty when s > smax)
+    const int jLast = min(RW - 1, a.smax - sFirst);  // last worker with a strip
+    const int sLast = sFirst + RW - 1;
+    const bool hasLeft = sFirst > 0, hasRight = sLast < a.smax;
+    const int y0F = y0of(sFirst), y1F = y1of(sFirst);
+    const int y0L = y0of(sLast), y1L = y1of(sLast);
+    const int y1p = hasLeft ? y1of(sFirst - 1) : -1;  // last row of the strip left of worker 0
+    const bool leftGlobal = hasLeft && warp == 0, rightGlobal = hasRight && warp == NW - 1;
+    const int Tbeg = y0F - 1, Tend = y1of(sFirst + jLast) + jLast;
+
+    const uint4* Cf = a.C + (size_t)frame * a.frameU4 + gl * NV;
+    uint4* Sf = a.S + (size_t)frame * a.frameU4 + gl * NV;
+    const int stepX = a.flip ? -a.pixU4 : a.pixU4;
+    const uint4* gin = nullptr;
+    uint4* gout = nullptr;
+    const int* gflagIn = nullptr;
+    int* gflagOut = nullptr;
+    if (leftGlobal) {
+      gin = a.edges + ((size_t)frame * (a.G - 1) + (sg - 1)) * (size_t)H * ENT;
+      gflagIn = a.gprog + frame * a.G + (sg - 1);
+    }
+    if (rightGlobal) {
+      gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * ENT;
+      gflagOut = a.gprog + frame * a.G + sg;
+    }
+    int loaded = max(y0F - 1, 0), gseen = 0, gpend = 0;
+
+    // ---- per-task register state
+    uint32_t Hs[kNR], Vd1[kNR], DLd1[kNR], DLd2[kNR];
+    uint32_t mH = 0, mVd1 = 0, mDLd1 = 0, mDLd2 = 0;
+    uint32_t recM[kK][3];   // mins of the records in the row buffer
+    uint4 cb[kK][NV], sb[kK][NV];  // C (and S of pass 1) of this chunk, loaded one chunk ahead
+#pragma unroll
+    for (int q = 0; q < kNR; q++) Hs[q] = Vd1[q] = DLd1[q] = DLd2[q] = 0;
+#pragma unroll
+    for (int i = 0; i < kK; i++) {
+      recM[i][0] = recM[i][1] = recM[i][2] = 0;
+#pragma unroll
+      for (int h = 0; h < NV; h++) cb[i][h] = sb[i][h] = make_uint4(0, 0, 0, 0);
+    }
+
+    bool ok = true;
+    for (int T = Tbeg; T <= Tend && ok; T++) {
+      const int r = T - j;                               // row of this worker
+      const bool act = r >= y0 && r <= y1;
+      const int xl = s * kK - r;                         // leftmost column of the chunk
+      const bool act0 = T >= y0F && T <= y1F;            // worker 0 of the warp has a row
+      const int rL = T - (RW - 1);
+      const bool actL = rL >= y0L && rL <= y1L;          // worker RW-1 has a row (and a strip)
+      // ================================================================== phase A: hand-over in
+      if (hasLeft && act0) {
+        const int need = min(T, y1p) + 1;
+        if (!leftGlobal) {
+          ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status);
+        } else {
+          gseen = max(gseen, gpend);
+          const bool blocking = loaded < need;
+          if (blocking) {
+            int n = 0;
+            while (gseen < need) {
+              gseen = ld_acquire_gpu(gflagIn);
+              if (gseen < need) {
+                __nanosleep(64);
+                if (((++n) & 255) == 0) {
+                  if (*sAbort || *(volatile int*)a.status) { *sAbort = 1; ok = false; break; }
+                  if (n > (kSpinLimit >> 4)) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
+                }
+              }
+            }
+          }
+          if (ok) {
+            // entries T-1 and T are in use; slots of rows up to T+2 are free
+            const int tgt = min(min(gseen, T + 3), y1p + 1);
+            for (int rr = loaded; rr < tgt; rr++) {
+              uint4* dst = ring0 + (rr & (kRingX - 1)) * ENT;
+              const uint4* src = gin + (size_t)rr * ENT;
+              for (int q = lane; q < ENT; q += 32) cp_async16(dst + q, src + q);
+            }
+            loaded = max(loaded, tgt);
+            if (blocking) cp_async_wait_all();
+            if (gseen < y1p + 1) gpend = ld_acquire_gpu(gflagIn);  // consumed in the next step
+          }
+        }
+      }
+      if (hasRight && actL && !rightGlobal && ok) ok = wait_cta(&sCons[warp + 1], rL - 2, sAbort, a.status);
+      if (!ok) break;
+      if (leftGlobal) cp_async_wait_all();  // prefetched entries of earlier steps have had a whole step to land
+      __syncwarp();
+      {
+        const uint4* eH = inRing + (r & inMask) * ENT + gl;
+        const uint4* eR = inRing + ((r - 1) & inMask) * ENT + gl;
+#pragma unroll
+        for (int h = 0; h < NV; h++) {
+          const uint4 v = eH[0 * VEC + h * LPP];
+          Hs[4 * h] = v.x; Hs[4 * h + 1] = v.y; Hs[4 * h + 2] = v.z; Hs[4 * h + 3] = v.w;
+          if (HAS_V) { const uint4 u = eR[1 * VEC + h * LPP]; Vd1[4 * h] = u.x; Vd1[4 * h + 1] = u.y; Vd1[4 * h + 2] = u.z; Vd1[4 * h + 3] = u.w; }
+          if (HAS_DL) {
+            const uint4 u = eR[2 * VEC + h * LPP]; DLd1[4 * h] = u.x; DLd1[4 * h + 1] = u.y; DLd1[4 * h + 2] = u.z; DLd1[4 * h + 3] = u.w;
+            const uint4 w = eR[3 * VEC + h * LPP]; DLd2[4 * h] = w.x; DLd2[4 * h + 1] = w.y; DLd2[4 * h + 2] = w.z; DLd2[4 * h + 3] = w.w;
+          }
+        }
+        mH = (inRing + (r & inMask) * ENT)[4 * VEC].x;
+        if (VERT) { const uint4 m = (inRing + ((r - 1) & inMask) * ENT)[4 * VEC]; mVd1 = m.y; mDLd1 = m.z; mDLd2 = m.w; }
+      }
+      __syncwarp();
+      // ================================================================== phase B: kK pixels
+      const int yp = a.flip ? H - 1 - r : r;
+      const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
+      const bool actn = (r + 1) >= y0 && (r + 1) <= y1;
+      const bool top = r == 0;
+      uint4* eOut = outRing + (r & outMask) * ENT + gl;
+      const bool expRing = (j < RW - 1) || (hasRight && act && !rightGlobal);
+      const bool expGlobal = (j == RW - 1) && rightGlobal && act;
+      uint4* gOut = expGlobal ? gout + (size_t)r * ENT + gl : nullptr;
+      uint32_t mDLprev = 0;
+#pragma unroll
+      for (int i = 0; i < kK; i++) {
+        const int x = xl + i;
+        const bool on = act && (unsigned)x < (unsigned)W1;
+        const int xp = a.flip ? W1 - 1 - x : x;
+        // ---- operands of this pixel were loaded one chunk ago; fetch those of the pixel below-left now
+        uint32_t c[kNR], sin[kNR];
+#pragma unroll
+        for (int h = 0; h < NV; h++) {
+          c[4 * h] = cb[i][h].x; c[4 * h + 1] = cb[i][h].y; c[4 * h + 2] = cb[i][h].z; c[4 * h + 3] = cb[i][h].w;
+          if (SECOND) { sin[4 * h] = sb[i][h].x; sin[4 * h + 1] = sb[i][h].y; sin[4 * h + 2] = sb[i][h].z; sin[4 * h + 3] = sb[i][h].w; }
+        }
+        {
+          const int xn = x - 1;
+          if (actn && active && (unsigned)xn < (unsigned)W1) {
+            const int xpn = a.flip ? W1 - 1 - xn : xn;
+            const unsigned off = (unsigned)ypn * a.rowU4 + (unsigned)xpn * (unsigned)a.pixU4;
+#pragma unroll
+            for (int h = 0; h < NV; h++) {
+              cb[i][h] = __ldcs(Cf + off + h);
+              if (SECOND) sb[i][h] = __ldcs(Sf + off + h);
+            }
+          }
+        }
+        // ---- old record of this slot: DR is used now, V one pixel later, DL two pixels later
+        uint32_t oV[kNR], oDL[kNR], DRin[kNR];
+        uint4* rec = rowbuf + i * REC;
+#pragma unroll
+        for (int h = 0; h < NV; h++) {
+          if (HAS_V) { const uint4 v = rec[0 * VEC + h * LPP]; oV[4 * h] = v.x; oV[4 * h + 1] = v.y; oV[4 * h + 2] = v.z; oV[4 * h + 3] = v.w; }
+          if (HAS_DL) { const uint4 v = rec[1 * VEC + h * LPP]; oDL[4 * h] = v.x; oDL[4 * h + 1] = v.y; oDL[4 * h + 2] = v.z; oDL[4 * h + 3] = v.w; }
+          if (HAS_DR) { const uint4 v = rec[2 * VEC + h * LPP]; DRin[4 * h] = v.x; DRin[4 * h + 1] = v.y; DRin[4 * h + 2] = v.z; DRin[4 * h + 3] = v.w; }
+        }
+        const uint32_t omV = recM[i][0], omDL = recM[i][1];
+        uint32_t mDR = recM[i][2];
+        // ---- the min-plus steps (A.5); a predecessor outside the volume is expressed through the scalars
+        sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+        uint32_t sum[kNR];
+#pragma unroll
+        for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
+        uint32_t mV = mVd1, mDL = mDLd2;
+        if (HAS_V) {
+          sweep_path_step<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], Vd1[q], kMax2);
+        }
+        if (HAS_DL) {
+          sweep_path_step<LPP>(DLd2, mDL, !on || top || x == 0, c, kc, gl, lastLane, active, lane);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DLd2[q], kMax2);
+        }
+        if (HAS_DR) {
+          sweep_path_step<LPP>(DRin, mDR, !on || top || x == W1 - 1, c, kc, gl, lastLane, active, lane);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DRin[q], kMax2);
+        }
+        // ---- new record of this slot (read by this worker in the next row)
+#pragma unroll
+        for (int h = 0; h < NV; h++) {
+          if (HAS_V) rec[0 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
+          if (HAS_DL) rec[1 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+          if (HAS_DR) rec[2 * VEC + h * LPP] = make_uint4(DRin[4 * h], DRin[4 * h + 1], DRin[4 * h + 2], DRin[4 * h + 3]);
+        }
+        recM[i][0] = mV; recM[i][1] = mDL; recM[i][2] = mDR;
+        // ---- hand-over to the right neighbour: the last two pixels of the chunk
+        if (i >= kK - 2) {
+          if (expRing) {
+#pragma unroll
+            for (int h = 0; h < NV; h++) {
+              if (i == kK - 2) {
+                if (HAS_DL) eOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+              } else {
+                eOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
+                if (HAS_V) eOut[1 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
+                if (HAS_DL) eOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+              }
+            }
+            if (i == kK - 1 && gl == 0) (eOut - gl)[4 * VEC] = make_uint4(mH, mV, mDL, mDLprev);
+          } else if (expGlobal) {
+#pragma unroll
+            for (int h = 0; h < NV; h++) {
+              if (i == kK - 2) {
+                if (HAS_DL) gOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+              } else {
+                gOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
+                if (HAS_V) gOut[1 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
+                if (HAS_DL) gOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+              }
+            }
+            if (i == kK - 1 && gl == 0) (gOut - gl)[4 * VEC] = make_uint4(mH, mV, mDL, mDLprev);
+          }
+          mDLprev = mDL;
+        }
+        // ---- output of the pixel
+        if (SECOND) {
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], sin[q], kMax2);
+          uint2 o;
+          sweep_wta<LPP>(sum, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
+          const unsigned off = (unsigned)yp * a.rowU4 + (unsigned)xp * (unsigned)a.pixU4;
+          if (on && gl == 0) a.sel[((size_t)frame * H + yp) * W1 + xp] = o;
+          if (a.debugS && on && active) {
+#pragma unroll
+            for (int h = 0; h < NV; h++) Sf[off + h] = make_uint4(sum[4 * h], sum[4 * h + 1], sum[4 * h + 2], sum[4 * h + 3]);
+          }
+        } else if (on && active) {
+          const unsigned off = (unsigned)yp * a.rowU4 + (unsigned)xp * (unsigned)a.pixU4;
+#pragma unroll
+          for (int h = 0; h < NV; h++) __stcs(Sf + off + h, make_uint4(sum[4 * h], sum[4 * h + 1], sum[4 * h + 2], sum[4 * h + 3]));
+        }
+        // ---- shift the delay line: what this slot held serves the next two pixels
+#pragma unroll
+        for (int q = 0; q < kNR; q++) {
+          if (HAS_DL) { DLd2[q] = DLd1[q]; DLd1[q] = oDL[q]; }
+          if (HAS_V) Vd1[q] = oV[q];
+        }
+        mDLd2 = mDLd1; mDLd1 = omDL; mVd1 = omV;
+      }
+      (void)stepX;
+      // ================================================================== hand-over out
+      __syncwarp();
+      if (lane == 0) {
+        if (act0) st_release_cta(&sCons[warp], T + 1);
+        if (actL && hasRight) {
+          if (rightGlobal) st_release_gpu(gflagOut, rL + 1);
+          else st_release_cta(&sProg[warp], rL + 1);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int lpp_of(int D) {
+  const int v = D / kDPL;
+  return v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : 16;
+}
+
+template <int LPP>
+struct Dims {
+  static int spc(bool second) { return second ? SweepGeom<LPP, true>::SPC : SweepGeom<LPP, false>::SPC; }
+  static int ent() { return SweepGeom<LPP, false>::ENT; }
+};
+int spc_of(int lpp, bool second) {
+  switch (lpp) {
+    case 1: return Dims<1>::spc(second);
+    case 2: return Dims<2>::spc(second);
+    case 4: return Dims<4>::spc(second);
+    case 8: return Dims<8>::spc(second);
+    default: return Dims<16>::spc(second);
+  }
+}
+int ent_of(int lpp) { return 4 * lpp * (kNR / 4) + 1; }
+int smax_of(const SgbmCfg& cfg) { return (cfg.W1 - 1 + cfg.H - 1) / kK; }
+int groups_of(const SgbmCfg& cfg, bool second) {
+  const int spc = spc_of(lpp_of(cfg.D), second);
+  return (smax_of(cfg) + 1 + spc - 1) / spc;
+}
+
+template <int LPP, int PATHS, bool SECOND>
+cudaError_t launch_one(const SweepArgs& a, int grid, cudaStream_t st) {
+  using G = SweepGeom<LPP, SECOND>;
+  auto* k = k_sweep<LPP, PATHS, SECOND>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+  if (e != cudaSuccess) return e;
+  k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int LPP>
+cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, int grid, cudaStream_t st) {
+  if (!second) {
+    if (paths == 15) return launch_one<LPP, 15, false>(a, grid, st);
+    return launch_one<LPP, P_H | P_V, false>(a, grid, st);
+  }
+  if (paths == 15) return launch_one<LPP, 15, true>(a, grid, st);
+  if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, true>(a, grid, st);
+  return launch_one<LPP, P_H, true>(a, grid, st);
+}
+
+}  // namespace
+
+size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
+  if (cfg.W1 <= 0) return 256;
+  return ((size_t)nframes * std::max(groups_of(cfg, false), groups_of(cfg, true)) + 64) * sizeof(int);
+}
+size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
+  if (cfg.W1 <= 0) return 256;
+  const int g = std::max(groups_of(cfg, false), groups_of(cfg, true));
+  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
+}
+
+// Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
+cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
+                                 LaunchStats* stats) {
+  static int numSM = 0;
+  if (!numSM) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);
+  }
+  SweepArgs a{};
+  a.C = (const uint4*)sc.C; a.S = (uint4*)sc.S; a.sel = (uint2*)sc.sel;
+  a.edges = (uint4*)sc.edges;
+  a.ticket = (int*)sc.flags;
+  a.gprog = (int*)sc.flags + 64;
+  a.status = sc.status;
+  a.W1 = cfg.W1; a.H = cfg.H; a.D = cfg.D; a.nAct = cfg.D / kDPL;
+  a.nframes = nframes; a.smax = smax_of(cfg); a.debugS = debugS;
+  a.frameU4 = (unsigned)(sc.frameCells / 8);
+  a.pixU4 = cfg.D / 8;
+  a.rowU4 = (unsigned)cfg.W1 * (unsigned)a.pixU4;
+  a.p1dup = dup16((uint32_t)cfg.P1);
+  a.p2mp1dup = dup16((uint32_t)(cfg.P2 - cfg.P1));
+  a.negp1dup = dup16((uint32_t)(-cfg.P1) & 0xFFFFu);
+  a.uniqF = 100 - cfg.uniq;
+  a.uniqMagic = a.uniqF >= 2 ? (uint32_t)((0x100000000ull + a.uniqF - 1) / a.uniqF) : 0u;
+  const int pass1 = cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : 15;
+  const int pass2 = cfg.mode == SV_MODE_HH ? 15 : (cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : P_H);
+  const int lpp = lpp_of(cfg.D);
+  for (int pass = 0; pass < 2; pass++) {
+    a.G = groups_of(cfg, pass == 1);
+    const size_t flagBytes = ((size_t)nframes * a.G + 64) * sizeof(int);
+    cudaError_t e = cudaMemsetAsync(sc.flags, 0, flagBytes, st);
+    if (e != cudaSuccess) return e;
+    a.flip = pass;
+    const int paths = pass ? pass2 : pass1;
+    const int grid = std::min(nframes * a.G, numSM);
+    switch (lpp) {
+      case 1: e = launch_lpp<1>(a, paths, pass == 1, grid, st); break;
+      case 2: e = launch_lpp<2>(a, paths, pass == 1, grid, st); break;
+      case 4: e = launch_lpp<4>(a, paths, pass == 1, grid, st); break;
+      case 8: e = launch_lpp<8>(a, paths, pass == 1, grid, st); break;
+      default: e = launch_lpp<16>(a, paths, pass == 1, grid, st); break;
+    }
+    if (stats) stats->launches++;
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace svgpu

@@ -24,7 +24,7 @@ EXPORTS = (
     "svgpu_set_bm", "svgpu_remap", "svgpu_sgbm_compute", "svgpu_sgbm_compute_batch", "svgpu_bm_compute",
     "svgpu_median3", "svgpu_filter_speckles", "svgpu_morph_close5", "svgpu_reproject", "svgpu_depth",
     "svgpu_prefilter_chain", "svgpu_resize", "svgpu_pipeline", "svgpu_debug_copy_volume", "svgpu_launch_count",
-    "svgpu_enable_stage_timing", "svgpu_last_stage_ms", "svgpu_set_sgbm_variant",
+    "svgpu_enable_stage_timing", "svgpu_last_stage_ms", "svgpu_debug_keep_volume",
 )
 
 
@@ -99,7 +99,7 @@ def load():
         "svgpu_launch_count": (C.c_longlong, [vp]),
         "svgpu_enable_stage_timing": (i, [vp, i]),
         "svgpu_last_stage_ms": (i, [vp, C.POINTER(C.c_float)]),
-        "svgpu_set_sgbm_variant": (i, [vp, i]),
+        "svgpu_debug_keep_volume": (i, [vp, i]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

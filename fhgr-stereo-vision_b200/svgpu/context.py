@@ -132,8 +132,8 @@ class Context:
         p = _abi.BmParams(**d)
         self._check(self._lib.svgpu_set_bm(self._h, C.byref(p)))
 
-    def set_sgbm_variant(self, v):
-        self._check(self._lib.svgpu_set_sgbm_variant(self._h, int(v)))
+    def debug_keep_volume(self, on=True):
+        self._check(self._lib.svgpu_debug_keep_volume(self._h, int(bool(on))))
 
     def enable_stage_timing(self, on=True):
         self._check(self._lib.svgpu_enable_stage_timing(self._h, int(bool(on))))

@@ -171,7 +171,7 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* ctx, const svgpu_pipeline_io* io, unsign
 
 /* ---- test hooks (used by tests/ to diff intermediates against the oracle) ------------- */
 /* copies the cost volume Ctrue (which=0) or the aggregated S (which=1) of pair 0 of the last
- * sgbm call to host: [H][W1][D] int16 */
+ * sgbm call to host: [H][W1][D] int16, disparities in natural order */
 SVGPU_API int svgpu_debug_copy_volume(svgpu_ctx* ctx, int which, int16_t* host_dst, size_t bytes);
 /* total number of kernel launches issued through this context so far */
 SVGPU_API long long svgpu_launch_count(const svgpu_ctx* ctx);
@@ -179,9 +179,9 @@ SVGPU_API long long svgpu_launch_count(const svgpu_ctx* ctx);
  * {pre-filter + cost volume, path aggregation, WTA + LR check + median, total} of the last sgbm call */
 SVGPU_API int svgpu_enable_stage_timing(svgpu_ctx* ctx, int on);
 SVGPU_API int svgpu_last_stage_ms(svgpu_ctx* ctx, float ms[4]);
-/* selects the aggregation schedule: -1 default, 0 one kernel per path direction,
- * 1 fused row sweeps. All schedules are bit-identical; this exists for tests and profiling. */
-SVGPU_API int svgpu_set_sgbm_variant(svgpu_ctx* ctx, int variant);
+/* when on, the second aggregation sweep also stores the final S volume so that
+ * svgpu_debug_copy_volume(which=1) returns the full sum over all paths (off: the sum of the first sweep) */
+SVGPU_API int svgpu_debug_keep_volume(svgpu_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

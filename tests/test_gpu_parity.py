@@ -25,9 +25,7 @@ def test_sgbm_golden_all_modes(svgpu):
     for i, l, r, prm, want in sgbm_golden_cases():
         with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
             ctx.set_sgbm(**prm)
-            for variant in (0, 1):
-                ctx.set_sgbm_variant(variant)
-                assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, variant, prm)
+            assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
 
 
 def test_sgbm_too_narrow_matches_reference_error(svgpu):
@@ -125,11 +123,9 @@ def test_device_memory_and_batch(svgpu, oracle):
         assert nmismatch(ctx.sgbm_batch(L, R), want) == 0  # host buffers
         tl, tr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        for variant in (0, 1):
-            ctx.set_sgbm_variant(variant)
-            td = ctx.sgbm_batch(tl, tr)
-            torch.cuda.synchronize()
-            assert nmismatch(td.cpu().numpy(), want) == 0, variant
+        td = ctx.sgbm_batch(tl, tr)
+        torch.cuda.synchronize()
+        assert nmismatch(td.cpu().numpy(), want) == 0
         one = ctx.sgbm(tl[2], tr[2])
         torch.cuda.synchronize()
         assert nmismatch(one.cpu().numpy(), want[2]) == 0

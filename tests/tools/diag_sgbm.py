@@ -12,7 +12,7 @@ from oracle import sv_oracle as O  # noqa: E402
 from svgpu.synth import synth_pair  # noqa: E402
 
 
-def run(H, W, D, mode, noise=False, variant=-1, **over):
+def run(H, W, D, mode, noise=False, **over):
     prm = dict(minDisparity=0, numDisparities=D, blockSize=7, P1=392, P2=1568, disp12MaxDiff=1, preFilterCap=32,
                uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, mode=mode)
     prm.update(over)
@@ -25,9 +25,9 @@ def run(H, W, D, mode, noise=False, variant=-1, **over):
     ref, Cv, Sv = O.sgbm_debug(l, r, **prm)
     ctx = svgpu.Context(W, H)
     ctx.set_sgbm(**prm)
-    ctx.set_sgbm_variant(variant)
+    ctx.debug_keep_volume(True)
     got = ctx.sgbm(l, r)
-    out = [f"H{H} W{W} D{D} mode{mode} noise{int(noise)} v{variant} {over}"]
+    out = [f"H{H} W{W} D{D} mode{mode} noise{int(noise)} {over}"]
     if Cv.size:
         gC = ctx.debug_volume(0, Cv.shape)
         gS = ctx.debug_volume(1, Sv.shape)
@@ -52,15 +52,14 @@ def run(H, W, D, mode, noise=False, variant=-1, **over):
 
 if __name__ == "__main__":
     bad = 0
-    V = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     for mode in (3, 0, 1):
-        bad += run(40, 120, 32, mode, variant=V)
-        bad += run(300, 500, 128, mode, variant=V)
-        bad += run(70, 300, 256, mode, variant=V)
-        bad += run(300, 120, 16, mode, variant=V)
-        bad += run(33, 100, 16, mode, variant=V, noise=True, blockSize=3, P1=8, P2=32, uniquenessRatio=0)
-        bad += run(61, 333, 64, mode, variant=V)
-        bad += run(50, 400, 224, mode, variant=V)
-        bad += run(37, 150, 48, mode, variant=V, minDisparity=4)
-        bad += run(37, 150, 48, mode, variant=V, minDisparity=-8, blockSize=5)
+        bad += run(40, 120, 32, mode)
+        bad += run(300, 500, 128, mode)
+        bad += run(70, 300, 256, mode)
+        bad += run(300, 120, 16, mode)
+        bad += run(33, 100, 16, mode, noise=True, blockSize=3, P1=8, P2=32, uniquenessRatio=0)
+        bad += run(61, 333, 64, mode)
+        bad += run(50, 400, 224, mode)
+        bad += run(37, 150, 48, mode, minDisparity=4)
+        bad += run(37, 150, 48, mode, minDisparity=-8, blockSize=5)
     print("TOTAL BAD", bad)
