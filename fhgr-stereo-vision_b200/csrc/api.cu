@@ -77,6 +77,21 @@ void free_scratch(svgpu_ctx* c) {
   c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0;
 }
 
+// the sweep kernels raise sc.status when a hand-over timed out (which would mean a scheduling bug or a device
+// fault); surfaced at every point where the host waits for the stream anyway
+int check_status(svgpu_ctx* c) {
+  if (!c->sc.status) return SV_OK;
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, c->sc.status, sizeof(int), cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+  if (e != cudaSuccess) return cuda_fail(c, e, "status read");
+  if (h) {
+    cudaMemsetAsync(c->sc.status, 0, sizeof(int), c->st);
+    return fail(c, SV_CUDA_ERROR, "sgbm aggregation sweep aborted (hand-over timed out)");
+  }
+  return SV_OK;
+}
+
 int ensure_scratch(svgpu_ctx* c, int batch) {
   const SgbmCfg& g = c->cfg;
   const size_t cells = g.W1 > 0 ? (size_t)g.W1 * g.H * g.D : 0;
@@ -98,6 +113,7 @@ int ensure_scratch(svgpu_ctx* c, int batch) {
   if (e != cudaSuccess) { free_scratch(c); return cuda_fail(c, e, "cudaMalloc(sgbm scratch)"); }
   cudaMemsetAsync(c->sc.status, 0, 256, c->st);
   cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(g, batch), c->st);
+  cudaMemsetAsync(c->sc.edges, 0, sgbm_edges_bytes(g, batch), c->st);  // launch tags start at 1
   c->sc.frameCells = cells;
   c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp;
   return SV_OK;
@@ -246,8 +262,10 @@ SVGPU_API int svgpu_reserve(svgpu_ctx* c, int maxBatch) {
 
 SVGPU_API int svgpu_sync(svgpu_ctx* c) {
   if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
   CU(c, cudaStreamSynchronize(c->st));
-  return SV_OK;
+  return check_status(c);
 }
 
 SVGPU_API const char* svgpu_last_error(const svgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -373,8 +391,7 @@ SVGPU_API int svgpu_sgbm_compute(svgpu_ctx* c, const uint8_t* left, size_t ls, c
     rc = run_sgbm(c, 1, (uint8_t*)c->stLeft.p, W, W * H, (uint8_t*)c->stRight.p, W, W * H, (int16_t*)c->stDisp.p, W * 2, W * H * 2);
     if (rc) return rc;
     rc = d2h_2d(c, disp, dstride, c->stDisp.p, W * 2, W * 2, (int)H); if (rc) return rc;
-    CU(c, cudaStreamSynchronize(c->st));
-    return SV_OK;
+    return check_status(c);
   }
   return run_sgbm(c, 1, left, ls, 0, right, rs, 0, disp, dstride, 0);
 }
@@ -405,7 +422,7 @@ SVGPU_API int svgpu_sgbm_compute_batch(svgpu_ctx* c, int n, const uint8_t* left,
       if (rc) return rc;
     }
   }
-  if (mem == SV_MEM_HOST) CU(c, cudaStreamSynchronize(c->st));
+  if (mem == SV_MEM_HOST) return check_status(c);
   return SV_OK;
 }
 
@@ -688,7 +705,7 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
     c->stats.launches++;
     if (host) { rc = d2h_2d(c, io->depth, io->depth_stride, o, os, W * 4, (int)H); if (rc) return rc; }
   }
-  if (host) CU(c, cudaStreamSynchronize(c->st));
+  if (host) return check_status(c);
   return SV_OK;
 }
 

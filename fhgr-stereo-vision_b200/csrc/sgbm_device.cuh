@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, int lane) {
 //          expressed through the two scalars only, so L may then hold any values in [0, 32767]
 //   c      Ctrue of this pixel
 // L(p,d) = C + min(L(q,d), L(q,d-1)+P1, L(q,d+1)+P1, m+P2) - m, evaluated as
-//   x = min3_s16(L(d-1), L(d+1), m+P2-P1);  y = min_u16(x+P1, L(d));  L' = y + C - m
+//   x = min3_s16(L(d-1), L(d+1), m+P2-P1);  y = min_u16(x+P1, L(d));  L' = y + C + (-m)
 // (3 instructions per packed register; no half ever borrows or carries because m <= y and y + C < 2^16).
 // ------------------------------------------------------------------------------------------------
 template <int LPP>
@@ -78,7 +78,7 @@ __device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& md
     if (gl == lastLane) dn = kMax2;  // L(q,D)  = MAX_COST
   }
   const uint32_t capm = outside ? k.negp1dup : mdup + k.p2mp1dup;
-  const uint32_t msub = outside ? 0u : mdup;
+  const uint32_t negm = outside ? 0u : 0u - mdup;
   const uint32_t lm0 = __byte_perm(up, L[kNR - 1], 0x5432);  // (d0-1, d0+7)
   const uint32_t lpN = __byte_perm(L[0], dn, 0x5432);        // (d0+8, d0+16)
   uint32_t n[kNR];
@@ -87,7 +87,7 @@ __device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& md
     const uint32_t lm = i ? L[i - 1] : lm0, lp = (i < kNR - 1) ? L[i + 1] : lpN;
     const uint32_t x = __vimin3_s16x2(lm, lp, capm);
     const uint32_t y = __viaddmin_u16x2(x, k.p1dup, L[i]);
-    n[i] = y + c[i] - msub;
+    n[i] = y + c[i] + negm;
   }
   uint32_t mn = __vimin3_u16x2(n[0], n[1], n[2]);
   mn = __vimin3_u16x2(mn, n[3], n[4]);

@@ -30,6 +30,7 @@
 // group interleaved (word i of a group = disparities d0+i and d0+i+8), so that the d-1 / d+1 neighbours of
 // a packed register are simply the previous / next register of the lane (sgbm_device.cuh).
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 #include "sgbm_device.cuh"
@@ -38,12 +39,26 @@ namespace svgpu {
 
 namespace {
 
-constexpr int kK = 4;          // strip width = pixels per chunk
+// compile-time tuning knobs (tools/build_variants.sh builds alternatives for A/B runs on the GPU)
+#ifndef SV_SWEEP_K
+#define SV_SWEEP_K 4
+#endif
+#ifndef SV_SWEEP_MAXNW
+#define SV_SWEEP_MAXNW 8
+#endif
+#ifndef SV_SWEEP_SLEEP
+#define SV_SWEEP_SLEEP 40
+#endif
+#ifndef SV_SWEEP_UNCOND
+#define SV_SWEEP_UNCOND 1
+#endif
+constexpr int kK = SV_SWEEP_K;  // strip width = pixels per chunk
 constexpr int kRingX = 4;      // entries in the import ring of a warp's first worker (fed by another warp / CTA)
 constexpr int kRingI = 2;      // entries in the import ring of the other workers (fed in lock step by the same warp)
-constexpr int kSpinLimit = 1 << 24;
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a hand-over that takes longer than this aborts the kernel
+constexpr int kFlagBytes = 256;   // hand-over counters, ticket and abort flag at the end of shared memory
 constexpr int kSmemMax = 227 * 1024;
-constexpr int kMaxNW = 8;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
+constexpr int kMaxNW = SV_SWEEP_MAXNW;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
 
 enum : int { P_H = 1, P_DL = 2, P_V = 4, P_DR = 8 };
 
@@ -60,18 +75,19 @@ struct SweepGeom {
   static constexpr int OFF_RING0 = OFF_RING + (RW - 1) * kRingI * ENT;
   static constexpr int OFF_WTA = OFF_RING0 + kRingX * ENT;
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
-  static constexpr int NW_FIT = (kSmemMax - 256) / (WARP_U4 * 16);
+  static constexpr int STAGE_U4 = 2 * ENT;         // one flag-in-data entry being fetched from the left CTA
+  static constexpr int NW_FIT = (kSmemMax - kFlagBytes - STAGE_U4 * 16) / (WARP_U4 * 16);
   static constexpr int NW = NW_FIT > kMaxNW ? kMaxNW : NW_FIT;  // warps per CTA
   static constexpr int SPC = NW * RW;             // strips per CTA task
-  static constexpr size_t SMEM = (size_t)NW * WARP_U4 * 16 + 256;
+  static constexpr size_t SMEM = (size_t)(NW * WARP_U4 + STAGE_U4) * 16 + kFlagBytes;
 };
 
 struct SweepArgs {
   const uint4* C;
   uint4* S;
   uint2* sel;     // [frame][H][W1]  pass 2: {reject<<31 | minS<<16 | best, S[best-1]<<16 | S[best+1]}
-  uint4* edges;   // [frame][G-1][H][ENT]
-  int* gprog;     // [frame][G]  rows of the strip group's last strip that are visible in `edges`
+  uint4* edges;   // [frame][G-1][H][2*ENT]  flag-in-data entries (see st_edge)
+  uint32_t tag;   // launch tag of the entries of this launch
   int* ticket;
   int* status;
   int W1, H, D, nAct;          // nAct = D/16 lanes of a worker hold disparities
@@ -84,49 +100,69 @@ struct SweepArgs {
   uint32_t uniqMagic;          // ceil(2^32 / uniqF) for uniqF >= 2
 };
 
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+// Hand-over counters between the warps of a CTA live in shared memory and are accessed with plain volatile
+// loads / stores: the shared-memory pipeline of an SM performs the accesses of a warp in program order, so the
+// ring entry written before the counter (same warp, after __syncwarp) is in place when another warp reads the
+// new counter value.  (A fence.cta here would also wait for the outstanding global prefetch loads of the
+// warp, i.e. expose a DRAM round trip in every step.)
+__device__ __forceinline__ int ld_flag(const int* p) {
   int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_flag(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Entries that cross a CTA boundary travel through global memory in "flag in data" form: every 16-byte store
+// carries two payload words and two copies of the launch tag, so the reader can tell a complete entry from a
+// stale or half-written one without any fence or separate flag.
+__device__ __forceinline__ uint4 ld_edge(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_edge(uint4* p, const uint4& v, uint32_t tag) {  // p -> two uint4 of the LL entry
+  __stcg(p, make_uint4(v.x, tag, v.y, tag));
+  __stcg(p + 1, make_uint4(v.z, tag, v.w, tag));
 }
 __device__ __forceinline__ void cp_async16(uint4* smemDst, const uint4* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// spin until *flag >= need; false when the kernel is being aborted
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *flag >= need, backing off between polls so that the warps sharing the scheduler keep their issue
+// slots; false when the kernel is being aborted
 __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int* sAbort, int* status) {
+  if (ld_flag(flag) >= need) return true;
+  unsigned long long t0 = 0;
   int n = 0;
-  while (ld_acquire_cta(flag) < need) {
-    if (((++n) & 1023) == 0) {
+  while (ld_flag(flag) < need) {
+    if (SV_SWEEP_SLEEP) __nanosleep(SV_SWEEP_SLEEP);
+    if (((++n) & 255) == 0) {
       if (*sAbort) return false;
-      if (n > kSpinLimit) { *sAbort = 1; atomicExch(status, 1); return false; }
+      if (!t0) t0 = now_ns();
+      if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(status, 1); return false; }
     }
   }
   return true;
 }
 
 template <int LPP, int PATHS, bool SECOND>
-__global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(const SweepArgs a) {
+__global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP, SECOND>::NW <= 4 ? 2 : 1) k_sweep(const SweepArgs a) {
   using G = SweepGeom<LPP, SECOND>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
   constexpr bool HAS_V = (PATHS & P_V) != 0, HAS_DL = (PATHS & P_DL) != 0, HAS_DR = (PATHS & P_DR) != 0;
   constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
   extern __shared__ uint4 smem[];
-  int* flags = (int*)(smem + NW * G::WARP_U4);
-  int* sProg = flags;            // [NW] rows exported by the last worker of warp w
-  int* sCons = flags + NW;       // [NW] rows finished by the first worker of warp w
+  uint4* stage = smem + NW * G::WARP_U4;
+  int* flags = (int*)(stage + G::STAGE_U4);
+  int* sProg = flags;            // [NW] rows exported by the last worker of warp w (last row + 1)
+  int* sCons = flags + NW;       // [NW] rows finished by the first worker of warp w (next row)
   int* sTicket = flags + 2 * NW;
   volatile int* sAbort = flags + 2 * NW + 1;
 
@@ -173,26 +209,20 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
     const bool hasLeft = sFirst > 0, hasRight = sLast < a.smax;
     const int y0F = y0of(sFirst), y1F = y1of(sFirst);
     const int y0L = y0of(sLast), y1L = y1of(sLast);
-    const int y1p = hasLeft ? y1of(sFirst - 1) : -1;  // last row of the strip left of worker 0
+    const int y0p = hasLeft ? y0of(sFirst - 1) : 0;   // rows of the strip left of worker 0: its entry k is row y0p + k
+    const int y1p = hasLeft ? y1of(sFirst - 1) : -1;
     const bool leftGlobal = hasLeft && warp == 0, rightGlobal = hasRight && warp == NW - 1;
     const int Tbeg = y0F - 1, Tend = y1of(sFirst + jLast) + jLast;
 
-    const uint4* Cf = a.C + (size_t)frame * a.frameU4 + gl * NV;
-    uint4* Sf = a.S + (size_t)frame * a.frameU4 + gl * NV;
-    const int stepX = a.flip ? -a.pixU4 : a.pixU4;
+    const int glc = active ? gl : 0;  // lanes without disparities load what lane 0 loads and store nothing
+    const uint4* Cf = a.C + (size_t)frame * a.frameU4 + glc * NV;
+    uint4* Sf = a.S + (size_t)frame * a.frameU4 + glc * NV;
     const uint4* gin = nullptr;
     uint4* gout = nullptr;
-    const int* gflagIn = nullptr;
-    int* gflagOut = nullptr;
-    if (leftGlobal) {
-      gin = a.edges + ((size_t)frame * (a.G - 1) + (sg - 1)) * (size_t)H * ENT;
-      gflagIn = a.gprog + frame * a.G + (sg - 1);
-    }
-    if (rightGlobal) {
-      gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * ENT;
-      gflagOut = a.gprog + frame * a.G + sg;
-    }
-    int loaded = max(y0F - 1, 0), gseen = 0, gpend = 0;
+    if (leftGlobal) gin = a.edges + ((size_t)frame * (a.G - 1) + (sg - 1)) * (size_t)H * (2 * ENT);
+    if (rightGlobal) gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * (2 * ENT);
+    int loaded = max(y0F - 1, 0);  // rows [.., loaded) of the left CTA's entries are in ring0
+    int pendRow = -1;              // row whose entry is on its way into `stage`
 
     // ---- per-task register state
     uint32_t Hs[kNR], Vd1[kNR], DLd1[kNR], DLd2[kNR];
@@ -208,8 +238,36 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
       for (int h = 0; h < NV; h++) cb[i][h] = sb[i][h] = make_uint4(0, 0, 0, 0);
     }
 
+    // moves one flag-in-data entry (global memory or `stage`) into a ring slot if every piece carries this
+    // launch's tag; all lanes of the warp call it, the result is warp-uniform
+    auto take_entry = [&](const uint4* src, uint4* dst, bool fromGlobal) -> bool {
+      constexpr int NIT = (ENT + 31) / 32;
+      uint4 d[NIT];
+      bool good = true;
+#pragma unroll
+      for (int it = 0; it < NIT; it++) {
+        const int q = lane + 32 * it;
+        if (q < ENT) {
+          const uint4 u = fromGlobal ? ld_edge(src + 2 * q) : src[2 * q], v = fromGlobal ? ld_edge(src + 2 * q + 1) : src[2 * q + 1];
+          good = good && u.y == a.tag && u.w == a.tag && v.y == a.tag && v.w == a.tag;
+          d[it] = make_uint4(u.x, u.z, v.x, v.z);
+        }
+      }
+      good = __all_sync(0xFFFFFFFFu, good);
+      if (good) {
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+          const int q = lane + 32 * it;
+          if (q < ENT) dst[q] = d[it];
+        }
+      }
+      return good;
+    };
+
     bool ok = true;
+    int where = 0, Tlast = 0;
     for (int T = Tbeg; T <= Tend && ok; T++) {
+      Tlast = T;
       const int r = T - j;                               // row of this worker
       const bool act = r >= y0 && r <= y1;
       const int xl = s * kK - r;                         // leftmost column of the chunk
@@ -219,41 +277,40 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
       // ================================================================== phase A: hand-over in
       if (hasLeft && act0) {
         const int need = min(T, y1p) + 1;
+        where = leftGlobal ? 3 : 1;
         if (!leftGlobal) {
           ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status);
         } else {
-          gseen = max(gseen, gpend);
-          const bool blocking = loaded < need;
-          if (blocking) {
-            int n = 0;
-            while (gseen < need) {
-              gseen = ld_acquire_gpu(gflagIn);
-              if (gseen < need) {
-                __nanosleep(64);
-                if (((++n) & 255) == 0) {
-                  if (*sAbort || *(volatile int*)a.status) { *sAbort = 1; ok = false; break; }
-                  if (n > (kSpinLimit >> 4)) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
-                }
-              }
+          // 1. the entry requested in the previous step has had a whole step to arrive in `stage`
+          if (pendRow >= 0) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (pendRow == loaded && take_entry(stage, ring0 + (pendRow & (kRingX - 1)) * ENT, false)) loaded++;
+            pendRow = -1;
+          }
+          // 2. rows needed now: fetch them directly, polling until the left CTA has written them
+          int n = 0;
+          unsigned long long t0 = 0;
+          while (loaded < need) {
+            if (take_entry(gin + (size_t)loaded * (2 * ENT), ring0 + (loaded & (kRingX - 1)) * ENT, true)) { loaded++; continue; }
+            __nanosleep(200);
+            if (((++n) & 63) == 0) {
+              if (!t0) t0 = now_ns();
+              if (*sAbort) { ok = false; break; }
+              if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
             }
           }
-          if (ok) {
-            // entries T-1 and T are in use; slots of rows up to T+2 are free
-            const int tgt = min(min(gseen, T + 3), y1p + 1);
-            for (int rr = loaded; rr < tgt; rr++) {
-              uint4* dst = ring0 + (rr & (kRingX - 1)) * ENT;
-              const uint4* src = gin + (size_t)rr * ENT;
-              for (int q = lane; q < ENT; q += 32) cp_async16(dst + q, src + q);
-            }
-            loaded = max(loaded, tgt);
-            if (blocking) cp_async_wait_all();
-            if (gseen < y1p + 1) gpend = ld_acquire_gpu(gflagIn);  // consumed in the next step
+          // 3. request the next row (entries T-1 and T are in use, so rows up to T+2 have a free slot)
+          if (ok && loaded <= min(T + 2, y1p)) {
+            const uint4* src = gin + (size_t)loaded * (2 * ENT);
+            for (int q = lane; q < 2 * ENT; q += 32) cp_async16(stage + q, src + q);
+            pendRow = loaded;
           }
         }
       }
-      if (hasRight && actL && !rightGlobal && ok) ok = wait_cta(&sCons[warp + 1], rL - 2, sAbort, a.status);
+      if (hasRight && actL && !rightGlobal && ok) { where = 2; ok = wait_cta(&sCons[warp + 1], rL - 3, sAbort, a.status); }
       if (!ok) break;
-      if (leftGlobal) cp_async_wait_all();  // prefetched entries of earlier steps have had a whole step to land
+      where = 0;
       __syncwarp();
       {
         const uint4* eH = inRing + (r & inMask) * ENT + gl;
@@ -268,10 +325,11 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
             const uint4 w = eR[3 * VEC + h * LPP]; DLd2[4 * h] = w.x; DLd2[4 * h + 1] = w.y; DLd2[4 * h + 2] = w.z; DLd2[4 * h + 3] = w.w;
           }
         }
-        mH = (inRing + (r & inMask) * ENT)[4 * VEC].x;
-        if (VERT) { const uint4 m = (inRing + ((r - 1) & inMask) * ENT)[4 * VEC]; mVd1 = m.y; mDLd1 = m.z; mDLd2 = m.w; }
+        mH = (eH - gl)[4 * VEC].x;
+        if (VERT) { const uint4 m = (eR - gl)[4 * VEC]; mVd1 = m.y; mDLd1 = m.z; mDLd2 = m.w; }
       }
       __syncwarp();
+      if (act0 && lane == 0) st_flag(&sCons[warp], T);  // rows < T are done with: their entries may be overwritten
       // ================================================================== phase B: kK pixels
       const int yp = a.flip ? H - 1 - r : r;
       const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
@@ -280,7 +338,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
       uint4* eOut = outRing + (r & outMask) * ENT + gl;
       const bool expRing = (j < RW - 1) || (hasRight && act && !rightGlobal);
       const bool expGlobal = (j == RW - 1) && rightGlobal && act;
-      uint4* gOut = expGlobal ? gout + (size_t)r * ENT + gl : nullptr;
+      uint4* gOut = expGlobal ? gout + (size_t)r * (2 * ENT) + 2 * gl : nullptr;
       uint32_t mDLprev = 0;
 #pragma unroll
       for (int i = 0; i < kK; i++) {
@@ -296,8 +354,18 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
         }
         {
           const int xn = x - 1;
-          if (actn && active && (unsigned)xn < (unsigned)W1) {
-            const int xpn = a.flip ? W1 - 1 - xn : xn;
+          const bool ld = actn && (unsigned)xn < (unsigned)W1;
+          const int xpn = a.flip ? W1 - 1 - xn : xn;
+#if SV_SWEEP_UNCOND
+          // always load (from a safe address when there is nothing to fetch) so that the data lands in cb/sb directly
+          const unsigned off = ld ? (unsigned)ypn * a.rowU4 + (unsigned)xpn * (unsigned)a.pixU4 : 0u;
+#pragma unroll
+          for (int h = 0; h < NV; h++) {
+            cb[i][h] = __ldcs(Cf + off + h);
+            if (SECOND) sb[i][h] = __ldcs(Sf + off + h);
+          }
+#else
+          if (ld) {
             const unsigned off = (unsigned)ypn * a.rowU4 + (unsigned)xpn * (unsigned)a.pixU4;
 #pragma unroll
             for (int h = 0; h < NV; h++) {
@@ -305,6 +373,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
               if (SECOND) sb[i][h] = __ldcs(Sf + off + h);
             }
           }
+#endif
         }
         // ---- old record of this slot: DR is used now, V one pixel later, DL two pixels later
         uint32_t oV[kNR], oDL[kNR], DRin[kNR];
@@ -364,14 +433,22 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
 #pragma unroll
             for (int h = 0; h < NV; h++) {
               if (i == kK - 2) {
-                if (HAS_DL) gOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+                if (HAS_DL) st_edge(gOut + 2 * (3 * VEC + h * LPP), make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]), a.tag);
               } else {
-                gOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
-                if (HAS_V) gOut[1 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
-                if (HAS_DL) gOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+                st_edge(gOut + 2 * (0 * VEC + h * LPP), make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]), a.tag);
+                if (HAS_V) st_edge(gOut + 2 * (1 * VEC + h * LPP), make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]), a.tag);
+                if (HAS_DL) st_edge(gOut + 2 * (2 * VEC + h * LPP), make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]), a.tag);
               }
             }
-            if (i == kK - 1 && gl == 0) (gOut - gl)[4 * VEC] = make_uint4(mH, mV, mDL, mDLprev);
+            if (i == kK - 1 && gl == 0) st_edge(gOut - 2 * gl + 2 * (4 * VEC), make_uint4(mH, mV, mDL, mDLprev), a.tag);
+            // paths this mode does not carry still need their tag: the reader validates the whole entry
+            if (i == kK - 1) {
+#pragma unroll
+              for (int h = 0; h < NV; h++) {
+                if (!HAS_V) st_edge(gOut + 2 * (1 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag);
+                if (!HAS_DL) { st_edge(gOut + 2 * (2 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag); st_edge(gOut + 2 * (3 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag); }
+              }
+            }
           }
           mDLprev = mDL;
         }
@@ -400,17 +477,13 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, 1) k_sweep(co
         }
         mDLd2 = mDLd1; mDLd1 = omDL; mVd1 = omV;
       }
-      (void)stepX;
       // ================================================================== hand-over out
       __syncwarp();
-      if (lane == 0) {
-        if (act0) st_release_cta(&sCons[warp], T + 1);
-        if (actL && hasRight) {
-          if (rightGlobal) st_release_gpu(gflagOut, rL + 1);
-          else st_release_cta(&sProg[warp], rL + 1);
-        }
-      }
+      if (lane == 0 && actL && hasRight && !rightGlobal) st_flag(&sProg[warp], rL + 1);
     }
+    if (!ok && lane == 0)
+      printf("svgpu sweep: cta %d warp %d task (frame %d, group %d) stopped at row step %d of [%d,%d] while waiting for %s\n", blockIdx.x, warp, frame, sg,
+             Tlast, Tbeg, Tend, where == 1 ? "left warp" : where == 2 ? "right warp" : where == 3 ? "left CTA" : "nothing");
   }
 }
 
@@ -466,20 +539,18 @@ cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, int grid, cud
 
 }  // namespace
 
-size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
-  if (cfg.W1 <= 0) return 256;
-  return ((size_t)nframes * std::max(groups_of(cfg, false), groups_of(cfg, true)) + 64) * sizeof(int);
-}
+size_t sgbm_flags_bytes(const SgbmCfg&, int) { return 256; }  // the ticket counter
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
   const int g = std::max(groups_of(cfg, false), groups_of(cfg, true));
-  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
+  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * 2 * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
 }
 
 // Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats) {
   static int numSM = 0;
+  static std::atomic<uint32_t> launchTag{0};
   if (!numSM) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -489,7 +560,6 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.C = (const uint4*)sc.C; a.S = (uint4*)sc.S; a.sel = (uint2*)sc.sel;
   a.edges = (uint4*)sc.edges;
   a.ticket = (int*)sc.flags;
-  a.gprog = (int*)sc.flags + 64;
   a.status = sc.status;
   a.W1 = cfg.W1; a.H = cfg.H; a.D = cfg.D; a.nAct = cfg.D / kDPL;
   a.nframes = nframes; a.smax = smax_of(cfg); a.debugS = debugS;
@@ -506,8 +576,9 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   const int lpp = lpp_of(cfg.D);
   for (int pass = 0; pass < 2; pass++) {
     a.G = groups_of(cfg, pass == 1);
-    const size_t flagBytes = ((size_t)nframes * a.G + 64) * sizeof(int);
-    cudaError_t e = cudaMemsetAsync(sc.flags, 0, flagBytes, st);
+    a.tag = ++launchTag;  // 0 is never used: the edge buffer starts out zeroed
+    if (a.tag == 0) a.tag = ++launchTag;
+    cudaError_t e = cudaMemsetAsync(sc.flags, 0, 256, st);
     if (e != cudaSuccess) return e;
     a.flip = pass;
     const int paths = pass ? pass2 : pass1;

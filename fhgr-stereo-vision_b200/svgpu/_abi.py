@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libsvgpu.so")
+# SVGPU_LIB: developer knob, path of another build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("SVGPU_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libsvgpu.so")
 
 SV_OK, SV_INVALID_IMAGE, SV_INVALID_SETTINGS, SV_CUDA_ERROR, SV_OOM, SV_NOT_CONFIGURED = 0, -1, -2, -3, -4, -5
 SV_MEM_HOST, SV_MEM_DEVICE = 0, 1
