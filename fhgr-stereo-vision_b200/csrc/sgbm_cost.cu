@@ -1,0 +1,262 @@
+// sgbm_cost.cu — SGBM matching cost volume: Birchfield-Tomasi pixel cost (A.3) + blockSize x blockSize box sum (A.4).
+//
+// Replaces the cost computation inside cv::StereoSGBM::compute (/root/reference/src/lib.cpp:262).  Input: the
+// pre-filter planes of both images (sgbm.cu: k_prefilter_planes); output: Ctrue[y][x'][d] uint16 in the
+// interleaved volume layout of sgbm_device.cuh (word i of a 16-disparity group = d0+i | (d0+i+8) << 16).
+//
+// One CTA produces a tile of NC - 2r output columns x a band of rows x all D disparities.
+//   pixel cost   thread (column c, group g of 16 disparities): lanes of a warp are neighbouring columns, so the
+//                right-image operands they read from shared memory are neighbouring 16-byte records.  Those
+//                records are staged per row with the two disparities of a packed register already paired
+//                (positions j and j+8) and with the negated copies the arithmetic needs, so that one cost of
+//                one channel is 5 packed instructions:
+//                    p = min(u - vhi, ulo - v), q = min(vlo - u, v - uhi), cost = max(0, p, q)
+//                (equal to min(max(0, u-vhi, vlo-u), max(0, v-uhi, ulo-v)) because vlo <= v <= vhi, ulo <= u <= uhi);
+//   vertical sum thread-private: the last 2r+1 rows of pixel costs sit packed as bytes in a register ring
+//                (the row loop is unrolled over the ring), the running sum Vs in 8 registers;
+//   horizontal   every kRB rows the Vs rows go through shared memory to a second thread mapping — lanes are
+//                (disparity half-group, row) pairs that slide a 2r+1 window along x — which writes C with
+//                256 contiguous bytes per pixel.
+// Columns are clamped in W1 coordinates and rows in image coordinates by computing the clamped position again
+// (A.4: the window replicates the border).
+#include <algorithm>
+
+#include "common.cuh"
+#include "sgbm_device.cuh"
+
+namespace svgpu {
+
+namespace {
+
+constexpr int kRB = 8;  // rows between two horizontal phases
+
+struct CostGeom {
+  int NJ;      // right-image records per row: reversed positions 0 .. NC + D + 7
+  int ng;      // groups of 16 disparities
+  int rowU4;   // uint4 per (row, half-group) line of the Vs buffer: NC + 1 (padding against bank conflicts)
+  size_t offL, offR, offV, total;  // byte offsets in dynamic shared memory
+};
+template <int NC>
+__host__ __device__ inline CostGeom cost_geom(int D) {
+  CostGeom g;
+  g.ng = D / kDPL;
+  g.NJ = NC + D + 8;
+  g.rowU4 = NC + 1;
+  g.offL = 0;                                        // [2 rows][2 channels][NC] uint4
+  g.offR = g.offL + (size_t)2 * 2 * NC * 16;         // [2 rows][2 channels][NJ] uint4
+  g.offV = g.offR + (size_t)2 * 2 * g.NJ * 16;       // [kRB][ng*2][NC+1] uint4
+  g.total = g.offV + (size_t)kRB * g.ng * 2 * g.rowU4 * 16;
+  return g;
+}
+
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// cost of one channel for two disparities: l = {ulo, u, -uhi, -u} (both halves equal), r = {-v, -vhi, v, vlo}
+__device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
+  const uint32_t p = __viaddmin_s16x2(r.y, l.y, __vadd2(r.x, l.x));  // min(u - vhi, ulo - v)
+  const uint32_t q = __viaddmin_s16x2(r.w, l.w, __vadd2(r.z, l.z));  // min(vlo - u, v - uhi)
+  return __vimax_s16x2_relu(p, q);
+}
+
+template <int R, int NC>
+__global__ void __launch_bounds__(512) k_cost_tile(const uint8_t* __restrict__ planesL, const uint8_t* __restrict__ planesR,
+                                                      uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
+  constexpr int NRING = 2 * R + 1, TW = NC - 2 * R;
+  extern __shared__ uint4 smemU4[];
+  const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
+  const CostGeom G = cost_geom<NC>(D);
+  uint4* sL = smemU4 + G.offL / 16;
+  uint4* sR = smemU4 + G.offR / 16;
+  uint4* sV = smemU4 + G.offV / 16;
+  const int NJ = G.NJ, ng = G.ng;
+
+  const int tid = threadIdx.x, nthr = blockDim.x;  // nthr = NC * ng
+  const int frame = blockIdx.z;
+  const int x0 = blockIdx.x * TW;                  // first output column x' of the tile
+  const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
+  const uint8_t* pL = planesL + (size_t)frame * H * 6 * Wp;
+  const uint8_t* pR = planesR + (size_t)frame * H * 6 * Wp;
+  uint4* Cf = Cvol + (size_t)frame * frameU4;
+
+  // ---- pixel-cost mapping
+  const int c = tid % NC, g = tid / NC;
+  const int ce = min(max(x0 - R + c, 0), W1 - 1) - (x0 - R);  // column whose costs this thread computes (border replicated)
+  const int j0 = (NC - 1 - ce) + kDPL * g;                    // reversed right-image position of (ce, d = 16 g)
+  const int xrMax = x0 - R + NC - 1 + cfg.minX1 - cfg.minD;   // right-image x of reversed position 0
+  // ---- horizontal mapping: lanes = (half-group, row), threads of one lane slot walk a run of columns
+  const int gh = tid % (ng * 2), hrow = (tid / (ng * 2)) % kRB, run = tid / (ng * 2 * kRB);
+  constexpr int NRUN = NC / 16, RL = (TW + NRUN - 1) / NRUN;
+
+  // ---- staging of the per-row operands: every thread owns up to kMaxItems records; the plane bytes are loaded
+  //      early (stage_load) and turned into records late (stage_store) so that the loads overlap the cost arithmetic
+  constexpr int kMaxItems = 5;  // (2 NC + 2 NJ) / (NC ng) <= 5 for every D
+  int itOffA[kMaxItems], itOffB[kMaxItems], itDst[kMaxItems];  // byte offsets inside the row's plane block (or -1), record index
+  uint32_t itLeft = 0;
+#pragma unroll
+  for (int q = 0; q < kMaxItems; q++) {
+    const int it = tid + q * nthr;
+    itOffA[q] = itOffB[q] = -1;
+    itDst[q] = -1;
+    if (it < 2 * NC) {
+      const int ch = it / NC, cc = it % NC;
+      itOffA[q] = 3 * ch * Wp + min(max(x0 - R + cc, 0), W1 - 1) + cfg.minX1;
+      itDst[q] = ch * NC + cc;
+      itLeft |= 1u << q;
+    } else if (it < 2 * NC + 2 * NJ) {
+      const int k = it - 2 * NC, ch = k / NJ, j = k % NJ;
+      const int xa = xrMax - j, xb = xa - 8;
+      if (xa >= 0 && xa < cfg.W) itOffA[q] = 3 * ch * Wp + xa;
+      if (xb >= 0 && xb < cfg.W) itOffB[q] = 3 * ch * Wp + xb;
+      itDst[q] = ch * NJ + j;
+    }
+  }
+  uint32_t stA[kMaxItems], stB[kMaxItems];  // the three plane bytes of position a / b of each record
+  auto stage_load = [&](int yy) {
+    const uint8_t* rowL = pL + (size_t)yy * 6 * Wp;
+    const uint8_t* rowR = pR + (size_t)yy * 6 * Wp;
+#pragma unroll
+    for (int q = 0; q < kMaxItems; q++) {
+      const uint8_t* row = ((itLeft >> q) & 1) ? rowL : rowR;
+      stA[q] = stB[q] = 0;
+      if (itOffA[q] >= 0) { const uint8_t* p = row + itOffA[q]; stA[q] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + Wp) << 8) | ((uint32_t)__ldg(p + 2 * Wp) << 16); }
+      if (itOffB[q] >= 0) { const uint8_t* p = row + itOffB[q]; stB[q] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + Wp) << 8) | ((uint32_t)__ldg(p + 2 * Wp) << 16); }
+    }
+  };
+  auto stage_store = [&](int b) {
+#pragma unroll
+    for (int q = 0; q < kMaxItems; q++) {
+      if (itDst[q] < 0) continue;
+      const int va = stA[q] & 0xFF, vloa = (stA[q] >> 8) & 0xFF, vhia = (stA[q] >> 16) & 0xFF;
+      const int vb = stB[q] & 0xFF, vlob = (stB[q] >> 8) & 0xFF, vhib = (stB[q] >> 16) & 0xFF;
+      if ((itLeft >> q) & 1)
+        sL[b * 2 * NC + itDst[q]] = make_uint4(dup16(vloa), dup16(va), dup16((uint32_t)(-vhia) & 0xFFFFu), dup16((uint32_t)(-va) & 0xFFFFu));
+      else
+        sR[b * 2 * NJ + itDst[q]] = make_uint4(pack16(-va, -vb), pack16(-vhia, -vhib), pack16(va, vb), pack16(vloa, vlob));
+    }
+  };
+
+  uint32_t Vs[kNR], pix[kNR], ring[NRING][kNR / 2];
+#pragma unroll
+  for (int i = 0; i < kNR; i++) Vs[i] = pix[i] = 0;
+#pragma unroll
+  for (int k = 0; k < NRING; k++)
+#pragma unroll
+    for (int i = 0; i < kNR / 2; i++) ring[k][i] = 0;
+
+  const int vbeg = yb - R, vend = ye - 1 + R;  // virtual rows whose pixel costs enter the band's sums
+  int staged = min(max(vbeg, 0), H - 1);       // image row in buffer (staged & 1)
+  stage_load(staged);
+  stage_store(staged & 1);
+  __syncthreads();
+  int computed = -1;                            // image row whose pixel costs are in `pix`
+
+  for (int v0 = vbeg; v0 <= vend; v0 += NRING) {
+#pragma unroll
+    for (int k = 0; k < NRING; k++) {
+      const int v = v0 + k;
+      if (v > vend) break;
+      const int yy = min(max(v, 0), H - 1);
+      // ---- the next image row is staged while this one is consumed: loads now, records after the arithmetic
+      const int ynext = min(max(v + 1, 0), H - 1);
+      const bool doStage = v < vend && ynext != staged;
+      if (doStage) stage_load(ynext);
+      // ---- pixel costs of image row yy (rows beyond the image border repeat the border row)
+      if (yy != computed) {
+        const uint4* lG = sL + ((yy & 1) * 2 + 0) * NC + ce;
+        const uint4* lI = sL + ((yy & 1) * 2 + 1) * NC + ce;
+        const uint4* rG = sR + ((yy & 1) * 2 + 0) * NJ + j0;
+        const uint4* rI = sR + ((yy & 1) * 2 + 1) * NJ + j0;
+        const uint4 ug = *lG, ui = *lI;
+#pragma unroll
+        for (int i = 0; i < kNR; i++) {
+          const uint32_t cg = bt_cost(ug, rG[i]);
+          const uint32_t ci = bt_cost(ui, rI[i]);
+          pix[i] = cg + ((ci >> 2) & 0x3FFF3FFFu);
+        }
+        computed = yy;
+      }
+      if (doStage) { stage_store(ynext & 1); staged = ynext; }
+      // ---- vertical running sum: + this row, - the row that leaves the window (ring slot k)
+#pragma unroll
+      for (int i = 0; i < kNR / 2; i++) {
+        const uint32_t old = ring[k][i];
+        Vs[2 * i] += pix[2 * i] - __byte_perm(old, 0, 0x4140);
+        Vs[2 * i + 1] += pix[2 * i + 1] - __byte_perm(old, 0, 0x4342);
+        ring[k][i] = __byte_perm(pix[2 * i], pix[2 * i + 1], 0x6420);
+      }
+      const int y = v - R;  // output row completed by this virtual row
+      if (y >= yb) {
+        uint4* dst = sV + ((size_t)((y - yb) % kRB) * ng * 2 + g * 2) * G.rowU4 + c;
+        dst[0] = make_uint4(Vs[0], Vs[1], Vs[2], Vs[3]);
+        dst[G.rowU4] = make_uint4(Vs[4], Vs[5], Vs[6], Vs[7]);
+      }
+      __syncthreads();  // staged operands and the Vs row are visible
+      if (y >= yb && (((y - yb) % kRB) == kRB - 1 || y == ye - 1)) {
+        // ---- horizontal window over the buffered Vs rows -> Ctrue
+        const int yrow = y - ((y - yb) % kRB) + hrow;  // image row of this thread's line
+        if (yrow <= y && run < NRUN) {
+          const bool zero = (cfg.mode == SV_MODE_HH4) && (yrow >= H - R);  // A.4: HH4 leaves the bottom rows at 0
+          const uint4* line = sV + ((size_t)hrow * ng * 2 + gh) * G.rowU4;
+          const int t0 = run * RL, t1 = min(min(t0 + RL, TW), W1 - x0);
+          if (t0 < t1) {
+            uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int dx = 0; dx < NRING; dx++) {
+              const uint4 q = line[t0 + dx];
+              acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            uint4* out = Cf + ((size_t)yrow * W1 + x0) * (D / 8) + gh;
+            for (int t = t0;; t++) {
+              __stcs(out + (size_t)t * (D / 8), zero ? make_uint4(0, 0, 0, 0) : acc);
+              if (t + 1 >= t1) break;
+              const uint4 in = line[t + NRING], ou = line[t];
+              acc.x += in.x - ou.x; acc.y += in.y - ou.y; acc.z += in.z - ou.z; acc.w += in.w - ou.w;
+            }
+          }
+        }
+        __syncthreads();  // the Vs buffer may be overwritten
+      }
+    }
+  }
+}
+
+template <int R, int NC>
+cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
+  const CostGeom G = cost_geom<NC>(cfg.D);
+  auto* k = k_cost_tile<R, NC>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
+  if (e != cudaSuccess) return e;
+  constexpr int TW = NC - 2 * R;
+  const int tiles = (cfg.W1 + TW - 1) / TW;
+  // bands: enough CTAs to fill the GPU a few times over, few enough that the 2r-row run-in stays small
+  int bands = (148 * 6 + tiles * nframes - 1) / (tiles * nframes);
+  bands = std::max(1, std::min(bands, (cfg.H + 63) / 64));
+  int rowsPerBand = (cfg.H + bands - 1) / bands;
+  rowsPerBand = (rowsPerBand + kRB - 1) / kRB * kRB;
+  bands = (cfg.H + rowsPerBand - 1) / rowsPerBand;
+  dim3 grid(tiles, bands, nframes);
+  k<<<grid, NC * (cfg.D / kDPL), G.total, st>>>(sc.planesL, sc.planesR, (uint4*)sc.C, cfg, rowsPerBand, sc.frameCells / 8);
+  return cudaGetLastError();
+}
+
+template <int NC>
+cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
+  switch (cfg.r) {
+    case 0: return launch_cost<0, NC>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC>(cfg, sc, nframes, st);
+    case 3: return launch_cost<3, NC>(cfg, sc, nframes, st);
+    case 4: return launch_cost<4, NC>(cfg, sc, nframes, st);
+    default: return launch_cost<5, NC>(cfg, sc, nframes, st);
+  }
+}
+
+}  // namespace
+
+// Ctrue of `nframes` pairs from their pre-filter planes
+cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
+  // 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
+  return cfg.D <= 128 ? launch_cost_r<64>(cfg, sc, nframes, st) : launch_cost_r<32>(cfg, sc, nframes, st);
+}
+
+}  // namespace svgpu
