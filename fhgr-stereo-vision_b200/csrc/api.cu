@@ -97,7 +97,7 @@ int ensure_scratch(svgpu_ctx* c, int batch) {
   const size_t cells = g.W1 > 0 ? (size_t)g.W1 * g.H * g.D : 0;
   if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->sc.dispRaw) return SV_OK;
   free_scratch(c);
-  const size_t planeBytes = (size_t)batch * g.H * 6 * g.Wp;
+  const size_t planeBytes = (size_t)batch * g.H * 2 * g.Wp * sizeof(uint2);
   const size_t w1 = g.W1 > 0 ? g.W1 : 0;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 256)); };

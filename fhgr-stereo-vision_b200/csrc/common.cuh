@@ -34,7 +34,7 @@ struct BmCfg {
 
 // Device buffers for `nframes` pairs in flight. Volumes are [frame][y][x'][d] uint16.
 struct SgbmScratch {
-  uint8_t* planesL;   // [frame][H][6][Wp]  g, glo, ghi, i, ilo, ihi
+  uint8_t* planesL;   // [frame][H][2][Wp] uint2  Birchfield-Tomasi operands per channel (sgbm.cu)
   uint8_t* planesR;
   uint16_t* C;        // cost volume Ctrue
   uint16_t* S;        // aggregated volume

@@ -6,7 +6,9 @@
 // Appendix A.1-A.7, which tests/ check bit-exactly against the cv2 binary.
 //
 // Data layout in HBM (per pair in flight):
-//   planes  [y][6][Wp] u8      pre-filter rows of one image: g, lo(g), hi(g), i, lo(i), hi(i)
+//   planes  [y][2][Wp] 2 x u32 Birchfield-Tomasi operands of one image per channel (gradient, intensity): for the
+//                              left image {lo | v<<16, -hi | -v<<16}, for the right image {-v | -hi<<16, v | lo<<16}
+//                              (16-bit fields), i.e. exactly the words the cost kernel pairs up (sgbm_cost.cu)
 //   C, S    [y][x'][d] u16     cost volume Ctrue and aggregated costs, d innermost so that one
 //                              pixel's D costs are D*2 contiguous bytes (256 B at D=128); inside each
 //                              group of 16 disparities the halves are interleaved (sgbm_device.cuh)
@@ -20,7 +22,7 @@
 namespace svgpu {
 
 // ------------------------------------------------------------------------------------------------
-// K1: pre-filter planes (A.2) + Birchfield-Tomasi half-pixel bounds (A.3)
+// K1: pre-filter (A.2) + Birchfield-Tomasi half-pixel bounds (A.3) -> operand planes
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int pf_grad(const uint8_t* r, const uint8_t* u, const uint8_t* d, int x, int W, int ftzero) {
   if (x <= 0 || x >= W - 1) return ftzero;
@@ -54,9 +56,15 @@ __global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restr
     const int g = (g0 + pf_grad(r, u, d, x + 1, W, ftzero)) >> 1, i = (i0 + pf_int(r, x + 1, W, ftzero)) >> 1;
     glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
   }
-  uint8_t* p = (side ? planesR : planesL) + ((size_t)frame * H + y) * 6 * Wp + x;
-  p[0] = (uint8_t)g0; p[Wp] = (uint8_t)glo; p[2 * Wp] = (uint8_t)ghi;
-  p[3 * Wp] = (uint8_t)i0; p[4 * Wp] = (uint8_t)ilo; p[5 * Wp] = (uint8_t)ihi;
+  auto h16 = [](int v) { return (uint32_t)v & 0xFFFFu; };
+  uint2* p = (uint2*)(side ? planesR : planesL) + ((size_t)frame * H + y) * 2 * Wp + x;
+  if (side == 0) {
+    p[0] = make_uint2(h16(glo) | h16(g0) << 16, h16(-ghi) | h16(-g0) << 16);
+    p[Wp] = make_uint2(h16(ilo) | h16(i0) << 16, h16(-ihi) | h16(-i0) << 16);
+  } else {
+    p[0] = make_uint2(h16(-g0) | h16(-ghi) << 16, h16(g0) | h16(glo) << 16);
+    p[Wp] = make_uint2(h16(-i0) | h16(-ihi) << 16, h16(i0) | h16(ilo) << 16);
+  }
 }
 
 // K5: sub-pixel disparity + left-right consistency check of one image row (A.6, second half), from the

@@ -1,7 +1,7 @@
 // sgbm_cost.cu — SGBM matching cost volume: Birchfield-Tomasi pixel cost (A.3) + blockSize x blockSize box sum (A.4).
 //
 // Replaces the cost computation inside cv::StereoSGBM::compute (/root/reference/src/lib.cpp:262).  Input: the
-// pre-filter planes of both images (sgbm.cu: k_prefilter_planes); output: Ctrue[y][x'][d] uint16 in the
+// Birchfield-Tomasi operand planes of both images (sgbm.cu: k_prefilter_planes); output: Ctrue[y][x'][d] uint16 in the
 // interleaved volume layout of sgbm_device.cuh (word i of a 16-disparity group = d0+i | (d0+i+8) << 16).
 //
 // One CTA produces a tile of NC - 2r output columns x a band of rows x all D disparities.
@@ -49,8 +49,6 @@ __host__ __device__ inline CostGeom cost_geom(int D) {
   return g;
 }
 
-__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
-
 // cost of one channel for two disparities: l = {ulo, u, -uhi, -u} (both halves equal), r = {-v, -vhi, v, vlo}
 __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
   const uint32_t p = __viaddmin_s16x2(r.y, l.y, __vadd2(r.x, l.x));  // min(u - vhi, ulo - v)
@@ -58,8 +56,8 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
   return __vimax_s16x2_relu(p, q);
 }
 
-template <int R, int NC>
-__global__ void __launch_bounds__(512) k_cost_tile(const uint8_t* __restrict__ planesL, const uint8_t* __restrict__ planesR,
+template <int R, int NC, int ITEMS>
+__global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
                                                       uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R;
   extern __shared__ uint4 smemU4[];
@@ -74,8 +72,8 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint8_t* __restrict__ p
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * TW;                  // first output column x' of the tile
   const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
-  const uint8_t* pL = planesL + (size_t)frame * H * 6 * Wp;
-  const uint8_t* pR = planesR + (size_t)frame * H * 6 * Wp;
+  const uint2* pL = planesL + (size_t)frame * H * 2 * Wp;
+  const uint2* pR = planesR + (size_t)frame * H * 2 * Wp;
   uint4* Cf = Cvol + (size_t)frame * frameU4;
 
   // ---- pixel-cost mapping
@@ -87,51 +85,55 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint8_t* __restrict__ p
   const int gh = tid % (ng * 2), hrow = (tid / (ng * 2)) % kRB, run = tid / (ng * 2 * kRB);
   constexpr int NRUN = NC / 16, RL = (TW + NRUN - 1) / NRUN;
 
-  // ---- staging of the per-row operands: every thread owns up to kMaxItems records; the plane bytes are loaded
-  //      early (stage_load) and turned into records late (stage_store) so that the loads overlap the cost arithmetic
-  constexpr int kMaxItems = 5;  // (2 NC + 2 NJ) / (NC ng) <= 5 for every D
-  int itOffA[kMaxItems], itOffB[kMaxItems], itDst[kMaxItems];  // byte offsets inside the row's plane block (or -1), record index
+  // ---- staging of the per-row operands: every thread owns up to ITEMS records; the operand words are loaded early
+  //      (stage_load) and paired into records late (stage_store) so that the loads overlap the cost arithmetic.
+  //      Left record of a column = the operand words with each 16-bit field doubled; right record of reversed
+  //      position j = the fields of positions j and j+8 side by side.
+  int itOffA[ITEMS], itOffB[ITEMS], itDst[ITEMS];  // operand index inside the row's plane block, record index (-1: none)
   uint32_t itLeft = 0;
 #pragma unroll
-  for (int q = 0; q < kMaxItems; q++) {
+  for (int q = 0; q < ITEMS; q++) {
     const int it = tid + q * nthr;
-    itOffA[q] = itOffB[q] = -1;
+    itOffA[q] = itOffB[q] = 0;
     itDst[q] = -1;
     if (it < 2 * NC) {
       const int ch = it / NC, cc = it % NC;
-      itOffA[q] = 3 * ch * Wp + min(max(x0 - R + cc, 0), W1 - 1) + cfg.minX1;
+      itOffA[q] = ch * Wp + min(max(x0 - R + cc, 0), W1 - 1) + cfg.minX1;
       itDst[q] = ch * NC + cc;
       itLeft |= 1u << q;
     } else if (it < 2 * NC + 2 * NJ) {
       const int k = it - 2 * NC, ch = k / NJ, j = k % NJ;
-      const int xa = xrMax - j, xb = xa - 8;
-      if (xa >= 0 && xa < cfg.W) itOffA[q] = 3 * ch * Wp + xa;
-      if (xb >= 0 && xb < cfg.W) itOffB[q] = 3 * ch * Wp + xb;
+      // positions outside the image only ever pair with cells outside the volume: any in-range word will do
+      itOffA[q] = ch * Wp + min(max(xrMax - j, 0), cfg.W - 1);
+      itOffB[q] = ch * Wp + min(max(xrMax - j - 8, 0), cfg.W - 1);
       itDst[q] = ch * NJ + j;
     }
   }
-  uint32_t stA[kMaxItems], stB[kMaxItems];  // the three plane bytes of position a / b of each record
+  uint2 stA[ITEMS], stB[ITEMS];
   auto stage_load = [&](int yy) {
-    const uint8_t* rowL = pL + (size_t)yy * 6 * Wp;
-    const uint8_t* rowR = pR + (size_t)yy * 6 * Wp;
+    const uint2* rowL = pL + (size_t)yy * 2 * Wp;
+    const uint2* rowR = pR + (size_t)yy * 2 * Wp;
 #pragma unroll
-    for (int q = 0; q < kMaxItems; q++) {
-      const uint8_t* row = ((itLeft >> q) & 1) ? rowL : rowR;
-      stA[q] = stB[q] = 0;
-      if (itOffA[q] >= 0) { const uint8_t* p = row + itOffA[q]; stA[q] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + Wp) << 8) | ((uint32_t)__ldg(p + 2 * Wp) << 16); }
-      if (itOffB[q] >= 0) { const uint8_t* p = row + itOffB[q]; stB[q] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + Wp) << 8) | ((uint32_t)__ldg(p + 2 * Wp) << 16); }
+    for (int q = 0; q < ITEMS; q++) {
+      if (itDst[q] < 0) continue;
+      if ((itLeft >> q) & 1) {
+        stA[q] = __ldg(rowL + itOffA[q]);
+      } else {
+        stA[q] = __ldg(rowR + itOffA[q]);
+        stB[q] = __ldg(rowR + itOffB[q]);
+      }
     }
   };
   auto stage_store = [&](int b) {
 #pragma unroll
-    for (int q = 0; q < kMaxItems; q++) {
+    for (int q = 0; q < ITEMS; q++) {
       if (itDst[q] < 0) continue;
-      const int va = stA[q] & 0xFF, vloa = (stA[q] >> 8) & 0xFF, vhia = (stA[q] >> 16) & 0xFF;
-      const int vb = stB[q] & 0xFF, vlob = (stB[q] >> 8) & 0xFF, vhib = (stB[q] >> 16) & 0xFF;
       if ((itLeft >> q) & 1)
-        sL[b * 2 * NC + itDst[q]] = make_uint4(dup16(vloa), dup16(va), dup16((uint32_t)(-vhia) & 0xFFFFu), dup16((uint32_t)(-va) & 0xFFFFu));
+        sL[b * 2 * NC + itDst[q]] = make_uint4(__byte_perm(stA[q].x, 0, 0x1010), __byte_perm(stA[q].x, 0, 0x3232),
+                                               __byte_perm(stA[q].y, 0, 0x1010), __byte_perm(stA[q].y, 0, 0x3232));
       else
-        sR[b * 2 * NJ + itDst[q]] = make_uint4(pack16(-va, -vb), pack16(-vhia, -vhib), pack16(va, vb), pack16(vloa, vlob));
+        sR[b * 2 * NJ + itDst[q]] = make_uint4(__byte_perm(stA[q].x, stB[q].x, 0x5410), __byte_perm(stA[q].x, stB[q].x, 0x7632),
+                                               __byte_perm(stA[q].y, stB[q].y, 0x5410), __byte_perm(stA[q].y, stB[q].y, 0x7632));
     }
   };
 
@@ -220,10 +222,10 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint8_t* __restrict__ p
   }
 }
 
-template <int R, int NC>
+template <int R, int NC, int ITEMS>
 cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
   const CostGeom G = cost_geom<NC>(cfg.D);
-  auto* k = k_cost_tile<R, NC>;
+  auto* k = k_cost_tile<R, NC, ITEMS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
@@ -235,19 +237,19 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, 
   rowsPerBand = (rowsPerBand + kRB - 1) / kRB * kRB;
   bands = (cfg.H + rowsPerBand - 1) / rowsPerBand;
   dim3 grid(tiles, bands, nframes);
-  k<<<grid, NC * (cfg.D / kDPL), G.total, st>>>(sc.planesL, sc.planesR, (uint4*)sc.C, cfg, rowsPerBand, sc.frameCells / 8);
+  k<<<grid, NC * (cfg.D / kDPL), G.total, st>>>((const uint2*)sc.planesL, (const uint2*)sc.planesR, (uint4*)sc.C, cfg, rowsPerBand, sc.frameCells / 8);
   return cudaGetLastError();
 }
 
-template <int NC>
+template <int NC, int ITEMS>
 cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC>(cfg, sc, nframes, st);
-    case 3: return launch_cost<3, NC>(cfg, sc, nframes, st);
-    case 4: return launch_cost<4, NC>(cfg, sc, nframes, st);
-    default: return launch_cost<5, NC>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, ITEMS>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, ITEMS>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, ITEMS>(cfg, sc, nframes, st);
+    case 3: return launch_cost<3, NC, ITEMS>(cfg, sc, nframes, st);
+    case 4: return launch_cost<4, NC, ITEMS>(cfg, sc, nframes, st);
+    default: return launch_cost<5, NC, ITEMS>(cfg, sc, nframes, st);
   }
 }
 
@@ -255,8 +257,11 @@ cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes
 
 // Ctrue of `nframes` pairs from their pre-filter planes
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
-  // 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
-  return cfg.D <= 128 ? launch_cost_r<64>(cfg, sc, nframes, st) : launch_cost_r<32>(cfg, sc, nframes, st);
+  // 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above; records staged per
+  // thread and row: (2 NC + 2 NJ) / threads, i.e. 2 except for the two smallest disparity ranges
+  if (cfg.D > 128) return launch_cost_r<32, 2>(cfg, sc, nframes, st);
+  if (cfg.D >= 48) return launch_cost_r<64, 2>(cfg, sc, nframes, st);
+  return launch_cost_r<64, 5>(cfg, sc, nframes, st);
 }
 
 }  // namespace svgpu
