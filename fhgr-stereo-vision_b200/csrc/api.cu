@@ -40,6 +40,11 @@ struct svgpu_ctx {
   Buf stLeft, stRight, stDisp, stXyz, stDepth, stRectL, stRectR, stGrayL, stGrayR, stTmpH, stTmpG, stDisp2, stLabels,
       stSizes, stSrc, stBmL, stBmR;
   int* minScratch = nullptr;
+  // streaming entry point: copy-in / compute / copy-out of consecutive enqueues overlap (double-buffered staging)
+  cudaStream_t stIn = nullptr, stOut = nullptr;
+  Buf pipeL[2], pipeR[2], pipeD[2];
+  cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+  unsigned long long enqueued = 0;
 
   LaunchStats stats;
   bool timing = false;
@@ -232,6 +237,12 @@ SVGPU_API int svgpu_destroy(svgpu_ctx* c) {
                             &c->stGrayR, &c->stTmpH, &c->stTmpG, &c->stDisp2, &c->stLabels, &c->stSizes, &c->stSrc, &c->stBmL, &c->stBmR})
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (int s = 0; s < 2; s++) {
+    release(c->pipeL[s]); release(c->pipeR[s]); release(c->pipeD[s]);
+    for (cudaEvent_t e : {c->evIn[s], c->evComp[s], c->evOut[s]}) if (e) cudaEventDestroy(e);
+  }
+  if (c->stIn) { cudaStreamSynchronize(c->stIn); cudaStreamDestroy(c->stIn); }
+  if (c->stOut) { cudaStreamSynchronize(c->stOut); cudaStreamDestroy(c->stOut); }
   if (c->own) cudaStreamDestroy(c->own);
   delete c;
   return SV_OK;
@@ -264,7 +275,9 @@ SVGPU_API int svgpu_sync(svgpu_ctx* c) {
   if (!c) return SV_INVALID_SETTINGS;
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
+  if (c->stIn) CU(c, cudaStreamSynchronize(c->stIn));
   CU(c, cudaStreamSynchronize(c->st));
+  if (c->stOut) CU(c, cudaStreamSynchronize(c->stOut));
   return check_status(c);
 }
 
@@ -423,6 +436,44 @@ SVGPU_API int svgpu_sgbm_compute_batch(svgpu_ctx* c, int n, const uint8_t* left,
     }
   }
   if (mem == SV_MEM_HOST) return check_status(c);
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_sgbm_enqueue_batch(svgpu_ctx* c, int n, const uint8_t* left, const uint8_t* right, int16_t* disp) {
+  if (!c) return SV_INVALID_SETTINGS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!left || !right || !disp || n <= 0) return fail(c, SV_INVALID_IMAGE, "empty batch");
+  if (!c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
+  if (n > c->maxBatch) return fail(c, SV_INVALID_SETTINGS, "enqueue_batch: n exceeds svgpu_reserve()");
+  cudaSetDevice(c->device);
+  const size_t W = c->W, H = c->H, img = W * H;
+  if (!c->stIn) {
+    CU(c, cudaStreamCreateWithFlags(&c->stIn, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->stOut, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++)
+      for (cudaEvent_t* e : {&c->evIn[s], &c->evComp[s], &c->evOut[s]}) CU(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  const int s = (int)(c->enqueued & 1);
+  int rc = ensure(c, c->pipeL[s], img * c->maxBatch); if (rc) return rc;
+  rc = ensure(c, c->pipeR[s], img * c->maxBatch); if (rc) return rc;
+  rc = ensure(c, c->pipeD[s], img * 2 * c->maxBatch); if (rc) return rc;
+  const bool reused = c->enqueued >= 2;  // slot s was used by the enqueue before the previous one
+  // copy-in: the kernels that read this staging slot last must be done
+  if (reused) CU(c, cudaStreamWaitEvent(c->stIn, c->evComp[s], 0));
+  CU(c, cudaMemcpyAsync(c->pipeL[s].p, left, img * n, cudaMemcpyHostToDevice, c->stIn));
+  CU(c, cudaMemcpyAsync(c->pipeR[s].p, right, img * n, cudaMemcpyHostToDevice, c->stIn));
+  CU(c, cudaEventRecord(c->evIn[s], c->stIn));
+  // kernels: inputs are in, and the copy-out that read this slot's result buffer last is done
+  CU(c, cudaStreamWaitEvent(c->st, c->evIn[s], 0));
+  if (reused) CU(c, cudaStreamWaitEvent(c->st, c->evOut[s], 0));
+  rc = run_sgbm(c, n, (uint8_t*)c->pipeL[s].p, W, img, (uint8_t*)c->pipeR[s].p, W, img, (int16_t*)c->pipeD[s].p, W * 2, img * 2);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->evComp[s], c->st));
+  // copy-out
+  CU(c, cudaStreamWaitEvent(c->stOut, c->evComp[s], 0));
+  CU(c, cudaMemcpyAsync(disp, c->pipeD[s].p, img * 2 * n, cudaMemcpyDeviceToHost, c->stOut));
+  CU(c, cudaEventRecord(c->evOut[s], c->stOut));
+  c->enqueued++;
   return SV_OK;
 }
 

@@ -22,7 +22,7 @@ STAGE_REMAP, STAGE_PREFILTER, STAGE_SGBM, STAGE_POSTFILTER, STAGE_REPROJECT, STA
 EXPORTS = (
     "svgpu_create", "svgpu_destroy", "svgpu_set_stream", "svgpu_use_own_stream", "svgpu_reserve", "svgpu_sync", "svgpu_last_error",
     "svgpu_version", "svgpu_set_rectify_maps", "svgpu_set_Q", "svgpu_set_depth_consts", "svgpu_set_sgbm",
-    "svgpu_set_bm", "svgpu_remap", "svgpu_sgbm_compute", "svgpu_sgbm_compute_batch", "svgpu_bm_compute",
+    "svgpu_set_bm", "svgpu_remap", "svgpu_sgbm_compute", "svgpu_sgbm_compute_batch", "svgpu_sgbm_enqueue_batch", "svgpu_bm_compute",
     "svgpu_median3", "svgpu_filter_speckles", "svgpu_morph_close5", "svgpu_reproject", "svgpu_depth",
     "svgpu_prefilter_chain", "svgpu_resize", "svgpu_pipeline", "svgpu_debug_copy_volume", "svgpu_launch_count",
     "svgpu_enable_stage_timing", "svgpu_last_stage_ms", "svgpu_debug_keep_volume",
@@ -87,6 +87,7 @@ def load():
         "svgpu_remap": (i, [vp, i, vp, i, i, sz, i, vp, sz, i]),
         "svgpu_sgbm_compute": (i, [vp, vp, sz, vp, sz, vp, sz, i]),
         "svgpu_sgbm_compute_batch": (i, [vp, i, vp, vp, vp, i]),
+        "svgpu_sgbm_enqueue_batch": (i, [vp, i, vp, vp, vp]),
         "svgpu_bm_compute": (i, [vp, vp, sz, vp, sz, vp, sz, i]),
         "svgpu_median3": (i, [vp, vp, sz, vp, sz, i]),
         "svgpu_filter_speckles": (i, [vp, vp, sz, i, i, i, i]),

@@ -184,6 +184,20 @@ class Context:
                                                        self._mem(left, right, disp)))
         return disp
 
+    def sgbm_enqueue(self, left, right, out):
+        """Streaming form of sgbm_batch for host (ideally pinned) arrays: returns at once; copy-in, kernels and copy-out of
+        consecutive calls overlap.  Keep the arrays alive and untouched until sync()."""
+        if _is_tensor(left) or _is_tensor(right) or _is_tensor(out):
+            raise ValueError("sgbm_enqueue takes host arrays")
+        for a, dt in ((left, np.uint8), (right, np.uint8), (out, np.int16)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("sgbm_enqueue needs contiguous uint8 inputs and an int16 output")
+        n = int(left.shape[0])
+        if tuple(left.shape[1:]) != (self.height, self.width) or tuple(right.shape) != tuple(left.shape) or tuple(out.shape) != tuple(left.shape):
+            raise ValueError("batch must be [n][H][W]")
+        self._keep = getattr(self, "_keep", [])[-8:] + [(left, right, out)]
+        self._check(self._lib.svgpu_sgbm_enqueue_batch(self._h, n, self._ptr(left), self._ptr(right), self._ptr(out)))
+
     def bm(self, left, right):
         """cv::StereoBM::compute — BASELINE config 2."""
         left, right = self._pair(left, right)

@@ -120,6 +120,11 @@ SVGPU_API int svgpu_sgbm_compute(svgpu_ctx* ctx, const uint8_t* left, size_t lef
  * throughput entry point the folder / livecam loops (static-image-main.cpp:107-127,
  * livecam-main.cpp:70-106) map onto. */
 SVGPU_API int svgpu_sgbm_compute_batch(svgpu_ctx* ctx, int n, const uint8_t* left, const uint8_t* right, int16_t* disp, int mem);
+/* Streaming form of the batch call for the livecam / folder loops (livecam-main.cpp:70-106,
+ * static-image-main.cpp:107-127): enqueues copy-in, kernels and copy-out of n <= svgpu_reserve() pairs in HOST memory
+ * (pinned for real overlap) and returns; consecutive enqueues overlap copy-in(k+1), kernels(k) and copy-out(k-1).
+ * The host buffers of a call must stay untouched until svgpu_sync(ctx) returns (which also reports errors). */
+SVGPU_API int svgpu_sgbm_enqueue_batch(svgpu_ctx* ctx, int n, const uint8_t* left, const uint8_t* right, int16_t* disp);
 /* cv::StereoBM::compute (BASELINE config 2) */
 SVGPU_API int svgpu_bm_compute(svgpu_ctx* ctx, const uint8_t* left, size_t left_stride, const uint8_t* right,
                      size_t right_stride, int16_t* disp, size_t disp_stride, int mem);

@@ -126,6 +126,14 @@ def test_device_memory_and_batch(svgpu, oracle):
         td = ctx.sgbm_batch(tl, tr)
         torch.cuda.synchronize()
         assert nmismatch(td.cpu().numpy(), want) == 0
+        # streaming entry point: three overlapping enqueues on rotating inputs, results read after sync()
+        outs = [np.zeros((3, H, W), np.int16) for _ in range(3)]
+        ins = [(np.ascontiguousarray(L[k:k + 3]), np.ascontiguousarray(R[k:k + 3])) for k in range(3)]
+        for k in range(3):
+            ctx.sgbm_enqueue(ins[k][0], ins[k][1], outs[k])
+        ctx.sync()
+        for k in range(3):
+            assert nmismatch(outs[k], want[k:k + 3]) == 0, k
         one = ctx.sgbm(tl[2], tr[2])
         torch.cuda.synchronize()
         assert nmismatch(one.cpu().numpy(), want[2]) == 0
