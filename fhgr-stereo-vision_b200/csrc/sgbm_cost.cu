@@ -24,28 +24,30 @@
 #include "common.cuh"
 #include "sgbm_device.cuh"
 
+#ifndef SV_COST_COLS
+#define SV_COST_COLS 1
+#endif
+
 namespace svgpu {
 
 namespace {
 
-constexpr int kRB = 8;  // rows between two horizontal phases
-
 struct CostGeom {
-  int NJ;      // right-image records per row: reversed positions 0 .. NC + D + 7
+  int NJ;      // right-image records per row: reversed positions 0 .. NC + D - 10
   int ng;      // groups of 16 disparities
   int rowU4;   // uint4 per (row, half-group) line of the Vs buffer: NC + 1 (padding against bank conflicts)
   size_t offL, offR, offV, total;  // byte offsets in dynamic shared memory
 };
-template <int NC>
+template <int NC, int RB>
 __host__ __device__ inline CostGeom cost_geom(int D) {
   CostGeom g;
   g.ng = D / kDPL;
-  g.NJ = NC + D + 8;
+  g.NJ = NC + D - 9;
   g.rowU4 = NC + 1;
   g.offL = 0;                                        // [2 rows][2 channels][NC] uint4
   g.offR = g.offL + (size_t)2 * 2 * NC * 16;         // [2 rows][2 channels][NJ] uint4
-  g.offV = g.offR + (size_t)2 * 2 * g.NJ * 16;       // [kRB][ng*2][NC+1] uint4
-  g.total = g.offV + (size_t)kRB * g.ng * 2 * g.rowU4 * 16;
+  g.offV = g.offR + (size_t)2 * 2 * g.NJ * 16;       // [RB][ng*2][NC+1] uint4
+  g.total = g.offV + (size_t)RB * g.ng * 2 * g.rowU4 * 16;
   return g;
 }
 
@@ -56,19 +58,21 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
   return __vimax_s16x2_relu(p, q);
 }
 
-template <int R, int NC, int ITEMS>
-__global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
-                                                      uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
-  constexpr int NRING = 2 * R + 1, TW = NC - 2 * R;
+// COLS neighbouring columns per thread: 8 of the 9 right-image records of two neighbouring columns are the same,
+// so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
+template <int R, int NC, int COLS, int RB, int ITEMS>
+__global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
+                                                                uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
+  constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
   extern __shared__ uint4 smemU4[];
   const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
-  const CostGeom G = cost_geom<NC>(D);
+  const CostGeom G = cost_geom<NC, RB>(D);
   uint4* sL = smemU4 + G.offL / 16;
   uint4* sR = smemU4 + G.offR / 16;
   uint4* sV = smemU4 + G.offV / 16;
   const int NJ = G.NJ, ng = G.ng;
 
-  const int tid = threadIdx.x, nthr = blockDim.x;  // nthr = NC * ng
+  const int tid = threadIdx.x, nthr = blockDim.x;  // nthr = NCP * ng
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * TW;                  // first output column x' of the tile
   const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
@@ -76,14 +80,19 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ pla
   const uint2* pR = planesR + (size_t)frame * H * 2 * Wp;
   uint4* Cf = Cvol + (size_t)frame * frameU4;
 
-  // ---- pixel-cost mapping
-  const int c = tid % NC, g = tid / NC;
-  const int ce = min(max(x0 - R + c, 0), W1 - 1) - (x0 - R);  // column whose costs this thread computes (border replicated)
-  const int j0 = (NC - 1 - ce) + kDPL * g;                    // reversed right-image position of (ce, d = 16 g)
+  // ---- pixel-cost mapping: lanes = neighbouring column groups, thread = (COLS columns, 16 disparities)
+  const int cp = tid % NCP, g = tid / NCP;
+  const int c0 = cp * COLS;                                   // first column of this thread (tile column 0 is x' = x0 - R)
+  const int j0 = (NC - COLS - c0) + kDPL * g;                 // reversed right-image position of (last column, d = 16 g)
   const int xrMax = x0 - R + NC - 1 + cfg.minX1 - cfg.minD;   // right-image x of reversed position 0
-  // ---- horizontal mapping: lanes = (half-group, row), threads of one lane slot walk a run of columns
-  const int gh = tid % (ng * 2), hrow = (tid / (ng * 2)) % kRB, run = tid / (ng * 2 * kRB);
-  constexpr int NRUN = NC / 16, RL = (TW + NRUN - 1) / NRUN;
+  // position of tile column c inside a line of the Vs buffer: the columns of one thread go to different planes so
+  // that the lanes of a warp store neighbouring words
+  auto vpos = [](int c) { return COLS == 1 ? c : (c % COLS) * NCP + c / COLS; };
+  // ---- horizontal mapping: lanes = (half-group, row), threads of one lane slot walk a run of columns.  The window
+  //      replicates the border columns of the volume (A.4): indices are clamped to the columns of x' = 0 .. W1-1
+  const int gh = tid % (ng * 2), hrow = (tid / (ng * 2)) % RB, run = tid / (ng * 2 * RB);
+  constexpr int NRUN = NC / (COLS * 2 * RB), RL = (TW + NRUN - 1) / NRUN;
+  const int cLo = max(R - x0, 0), cHi = min(W1 - 1 - x0 + R, NC - 1);
 
   // ---- staging of the per-row operands: every thread owns up to ITEMS records; the operand words are loaded early
   //      (stage_load) and paired into records late (stage_store) so that the loads overlap the cost arithmetic.
@@ -98,7 +107,8 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ pla
     itDst[q] = -1;
     if (it < 2 * NC) {
       const int ch = it / NC, cc = it % NC;
-      itOffA[q] = ch * Wp + min(max(x0 - R + cc, 0), W1 - 1) + cfg.minX1;
+      // columns outside the volume are computed on some valid pixel and ignored by the horizontal phase
+      itOffA[q] = ch * Wp + min(max(x0 - R + cc + cfg.minX1, 0), cfg.W - 1);
       itDst[q] = ch * NC + cc;
       itLeft |= 1u << q;
     } else if (it < 2 * NC + 2 * NJ) {
@@ -137,13 +147,16 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ pla
     }
   };
 
-  uint32_t Vs[kNR], pix[kNR], ring[NRING][kNR / 2];
+  uint32_t Vs[COLS][kNR], pix[COLS][kNR], ring[NRING][COLS][kNR / 2];
 #pragma unroll
-  for (int i = 0; i < kNR; i++) Vs[i] = pix[i] = 0;
+  for (int m = 0; m < COLS; m++) {
 #pragma unroll
-  for (int k = 0; k < NRING; k++)
+    for (int i = 0; i < kNR; i++) Vs[m][i] = pix[m][i] = 0;
 #pragma unroll
-    for (int i = 0; i < kNR / 2; i++) ring[k][i] = 0;
+    for (int k = 0; k < NRING; k++)
+#pragma unroll
+      for (int i = 0; i < kNR / 2; i++) ring[k][m][i] = 0;
+  }
 
   const int vbeg = yb - R, vend = ye - 1 + R;  // virtual rows whose pixel costs enter the band's sums
   int staged = min(max(vbeg, 0), H - 1);       // image row in buffer (staged & 1)
@@ -162,56 +175,71 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ pla
       const int ynext = min(max(v + 1, 0), H - 1);
       const bool doStage = v < vend && ynext != staged;
       if (doStage) stage_load(ynext);
-      // ---- pixel costs of image row yy (rows beyond the image border repeat the border row)
+      // ---- pixel costs of image row yy (rows beyond the image border repeat the border row).  Column c0 + m reads the
+      //      records j0 + (COLS-1-m) + i, i = 0..7: record q of this thread serves register q - (COLS-1-m) of column m
       if (yy != computed) {
-        const uint4* lG = sL + ((yy & 1) * 2 + 0) * NC + ce;
-        const uint4* lI = sL + ((yy & 1) * 2 + 1) * NC + ce;
-        const uint4* rG = sR + ((yy & 1) * 2 + 0) * NJ + j0;
-        const uint4* rI = sR + ((yy & 1) * 2 + 1) * NJ + j0;
-        const uint4 ug = *lG, ui = *lI;
 #pragma unroll
-        for (int i = 0; i < kNR; i++) {
-          const uint32_t cg = bt_cost(ug, rG[i]);
-          const uint32_t ci = bt_cost(ui, rI[i]);
-          pix[i] = cg + ((ci >> 2) & 0x3FFF3FFFu);
+        for (int ch = 0; ch < 2; ch++) {
+          const uint4* lrec = sL + ((yy & 1) * 2 + ch) * NC + c0;
+          const uint4* rrec = sR + ((yy & 1) * 2 + ch) * NJ + j0;
+          uint4 lu[COLS];
+#pragma unroll
+          for (int m = 0; m < COLS; m++) lu[m] = lrec[m];
+#pragma unroll
+          for (int q = 0; q < kNR + COLS - 1; q++) {
+            const uint4 rr = rrec[q];
+#pragma unroll
+            for (int m = 0; m < COLS; m++) {
+              const int i = q - (COLS - 1 - m);
+              if (i >= 0 && i < kNR) {
+                const uint32_t cst = bt_cost(lu[m], rr);
+                if (ch == 0) pix[m][i] = cst;
+                else pix[m][i] += (cst >> 2) & 0x3FFF3FFFu;
+              }
+            }
+          }
         }
         computed = yy;
       }
       if (doStage) { stage_store(ynext & 1); staged = ynext; }
       // ---- vertical running sum: + this row, - the row that leaves the window (ring slot k)
-#pragma unroll
-      for (int i = 0; i < kNR / 2; i++) {
-        const uint32_t old = ring[k][i];
-        Vs[2 * i] += pix[2 * i] - __byte_perm(old, 0, 0x4140);
-        Vs[2 * i + 1] += pix[2 * i + 1] - __byte_perm(old, 0, 0x4342);
-        ring[k][i] = __byte_perm(pix[2 * i], pix[2 * i + 1], 0x6420);
-      }
       const int y = v - R;  // output row completed by this virtual row
-      if (y >= yb) {
-        uint4* dst = sV + ((size_t)((y - yb) % kRB) * ng * 2 + g * 2) * G.rowU4 + c;
-        dst[0] = make_uint4(Vs[0], Vs[1], Vs[2], Vs[3]);
-        dst[G.rowU4] = make_uint4(Vs[4], Vs[5], Vs[6], Vs[7]);
+#pragma unroll
+      for (int m = 0; m < COLS; m++) {
+#pragma unroll
+        for (int i = 0; i < kNR / 2; i++) {
+          const uint32_t old = ring[k][m][i];
+          Vs[m][2 * i] += pix[m][2 * i] - __byte_perm(old, 0, 0x4140);
+          Vs[m][2 * i + 1] += pix[m][2 * i + 1] - __byte_perm(old, 0, 0x4342);
+          ring[k][m][i] = __byte_perm(pix[m][2 * i], pix[m][2 * i + 1], 0x6420);
+        }
+        if (y >= yb) {
+          uint4* dst = sV + ((size_t)((y - yb) % RB) * ng * 2 + g * 2) * G.rowU4 + vpos(c0 + m);
+          dst[0] = make_uint4(Vs[m][0], Vs[m][1], Vs[m][2], Vs[m][3]);
+          dst[G.rowU4] = make_uint4(Vs[m][4], Vs[m][5], Vs[m][6], Vs[m][7]);
+        }
       }
       __syncthreads();  // staged operands and the Vs row are visible
-      if (y >= yb && (((y - yb) % kRB) == kRB - 1 || y == ye - 1)) {
+      if (y >= yb && (((y - yb) % RB) == RB - 1 || y == ye - 1)) {
         // ---- horizontal window over the buffered Vs rows -> Ctrue
-        const int yrow = y - ((y - yb) % kRB) + hrow;  // image row of this thread's line
+        const int yrow = y - ((y - yb) % RB) + hrow;  // image row of this thread's line
         if (yrow <= y && run < NRUN) {
           const bool zero = (cfg.mode == SV_MODE_HH4) && (yrow >= H - R);  // A.4: HH4 leaves the bottom rows at 0
           const uint4* line = sV + ((size_t)hrow * ng * 2 + gh) * G.rowU4;
+          auto at = [&](int c) { return line[vpos(min(max(c, cLo), cHi))]; };
           const int t0 = run * RL, t1 = min(min(t0 + RL, TW), W1 - x0);
           if (t0 < t1) {
             uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int dx = 0; dx < NRING; dx++) {
-              const uint4 q = line[t0 + dx];
+              const uint4 q = at(t0 + dx);
               acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
             }
             uint4* out = Cf + ((size_t)yrow * W1 + x0) * (D / 8) + gh;
             for (int t = t0;; t++) {
               __stcs(out + (size_t)t * (D / 8), zero ? make_uint4(0, 0, 0, 0) : acc);
               if (t + 1 >= t1) break;
-              const uint4 in = line[t + NRING], ou = line[t];
+              const uint4 in = at(t + NRING), ou = at(t);
               acc.x += in.x - ou.x; acc.y += in.y - ou.y; acc.z += in.z - ou.z; acc.w += in.w - ou.w;
             }
           }
@@ -222,10 +250,10 @@ __global__ void __launch_bounds__(512) k_cost_tile(const uint2* __restrict__ pla
   }
 }
 
-template <int R, int NC, int ITEMS>
+template <int R, int NC, int COLS, int RB, int ITEMS>
 cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
-  const CostGeom G = cost_geom<NC>(cfg.D);
-  auto* k = k_cost_tile<R, NC, ITEMS>;
+  const CostGeom G = cost_geom<NC, RB>(cfg.D);
+  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
@@ -234,22 +262,23 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, 
   int bands = (148 * 6 + tiles * nframes - 1) / (tiles * nframes);
   bands = std::max(1, std::min(bands, (cfg.H + 63) / 64));
   int rowsPerBand = (cfg.H + bands - 1) / bands;
-  rowsPerBand = (rowsPerBand + kRB - 1) / kRB * kRB;
+  rowsPerBand = (rowsPerBand + RB - 1) / RB * RB;
   bands = (cfg.H + rowsPerBand - 1) / rowsPerBand;
   dim3 grid(tiles, bands, nframes);
-  k<<<grid, NC * (cfg.D / kDPL), G.total, st>>>((const uint2*)sc.planesL, (const uint2*)sc.planesR, (uint4*)sc.C, cfg, rowsPerBand, sc.frameCells / 8);
+  k<<<grid, (NC / COLS) * (cfg.D / kDPL), G.total, st>>>((const uint2*)sc.planesL, (const uint2*)sc.planesR, (uint4*)sc.C, cfg, rowsPerBand,
+                                                         sc.frameCells / 8);
   return cudaGetLastError();
 }
 
-template <int NC, int ITEMS>
+template <int NC, int COLS, int RB, int ITEMS>
 cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC, ITEMS>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC, ITEMS>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC, ITEMS>(cfg, sc, nframes, st);
-    case 3: return launch_cost<3, NC, ITEMS>(cfg, sc, nframes, st);
-    case 4: return launch_cost<4, NC, ITEMS>(cfg, sc, nframes, st);
-    default: return launch_cost<5, NC, ITEMS>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    case 3: return launch_cost<3, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    case 4: return launch_cost<4, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    default: return launch_cost<5, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
   }
 }
 
@@ -257,11 +286,20 @@ cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes
 
 // Ctrue of `nframes` pairs from their pre-filter planes
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
-  // 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above; records staged per
-  // thread and row: (2 NC + 2 NJ) / threads, i.e. 2 except for the two smallest disparity ranges
-  if (cfg.D > 128) return launch_cost_r<32, 2>(cfg, sc, nframes, st);
-  if (cfg.D >= 48) return launch_cost_r<64, 2>(cfg, sc, nframes, st);
-  return launch_cost_r<64, 5>(cfg, sc, nframes, st);
+  // records staged per thread and row = (2 NC + 2 NJ) / threads
+#if SV_COST_COLS == 2
+  // two columns per thread, 32 column pairs x D/16 groups <= 256 threads, two CTAs per SM
+  if (cfg.D > 128) return launch_cost_r<32, 2, 4, 3>(cfg, sc, nframes, st);   // 16 pairs x <= 16 groups
+  if (cfg.D == 128) return launch_cost_r<64, 2, 4, 2>(cfg, sc, nframes, st);
+  if (cfg.D >= 64) return launch_cost_r<64, 2, 4, 3>(cfg, sc, nframes, st);
+  return launch_cost_r<64, 2, 4, 9>(cfg, sc, nframes, st);
+#else
+  // one column per thread: 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
+  if (cfg.D > 128) return launch_cost_r<32, 1, 8, 2>(cfg, sc, nframes, st);
+  if (cfg.D == 128) return launch_cost_r<64, 1, 8, 1>(cfg, sc, nframes, st);
+  if (cfg.D >= 48) return launch_cost_r<64, 1, 8, 2>(cfg, sc, nframes, st);
+  return launch_cost_r<64, 1, 8, 5>(cfg, sc, nframes, st);
+#endif
 }
 
 }  // namespace svgpu
