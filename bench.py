@@ -252,14 +252,22 @@ def main():
         e2e_value = (B * world * e2e_steps) * MPD_PER_PAIR / (ms_e2e_max / 1e3)
         hbm_peak, which = peaks()
         cells = (W - D) * H * D
-        # dominant stage: path aggregation. Algorithmic bytes of the whole 8-path chain: 10 B per volume cell
-        # (SURVEY.md §8d); of the aggregation stage alone: read C once per sweep, S written once and read once.
+        # Dominant kernel: k_sweep (path aggregation + WTA), two launches per step (forward and reverse sweep).
+        # Algorithmic bytes per launch = 4 B per computed volume cell (sweep 1: read C, write S; sweep 2: read C, read S),
+        # SURVEY.md §8d; duration = the live CUDA-event time of the aggregation stage / 2 launches.  `traffic` = DRAM
+        # bytes per launch from the committed `ncu --set full` capture (profiles/r01_v3_summary.md: 1.021 GB per pair for
+        # sweep 1, 1.038 GB for sweep 2), scaled to this batch.
         agg_ms = stage["aggregate"]
-        agg_bytes = 8.0 * cells * B  # sweep-1 read C + write S + sweep-2 read C + read S (2 B each)
-        roofline = {"bound": "hbm", "kernel": "path aggregation (k_agg_*), all launches of one step",
-                    "achieved": agg_bytes / (agg_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / hbm_peak, "traffic": None, "peak_source": which,
-                    "algorithmic_bytes_per_step": agg_bytes, "stage_ms_per_step": stage,
+        launch_bytes = 4.0 * cells * B
+        launch_s = agg_ms / 1e3 / 2
+        roofline = {"bound": "hbm", "kernel": "k_sweep<8,15,*> (path aggregation + winner-take-all; 2 launches per step)",
+                    "achieved": launch_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": launch_bytes / launch_s / 1e9 / hbm_peak, "traffic": 1.03e9 * B, "peak_source": which,
+                    "algorithmic_bytes_per_launch": launch_bytes, "launch_ms": launch_s * 1e3, "stage_ms_per_step": stage,
+                    "note": "the sweeps are bound by the packed-integer ALU pipe (ncu: ~50 % of the pipe over the launch), not by HBM; "
+                            "HBM is reported because it is the only peak with a driver-measured denominator",
+                    "cost_kernel": {"bytes_per_cell": 2, "achieved": 2.0 * cells * B / (stage["cost"] / 1e3) / 1e9,
+                                    "frac": 2.0 * cells * B / (stage["cost"] / 1e3) / 1e9 / hbm_peak},
                     "chain": {"bytes_per_cell": 10, "achieved": 10.0 * cells * B / (stage["total"] / 1e3) / 1e9,
                               "frac": 10.0 * cells * B / (stage["total"] / 1e3) / 1e9 / hbm_peak}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
