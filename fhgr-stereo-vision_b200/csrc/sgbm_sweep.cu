@@ -49,6 +49,15 @@ namespace {
 #ifndef SV_SWEEP_SLEEP
 #define SV_SWEEP_SLEEP 40
 #endif
+#ifndef SV_SWEEP_PROF
+#define SV_SWEEP_PROF 0
+#endif
+#ifndef SV_SWEEP_BULK
+#define SV_SWEEP_BULK 1
+#endif
+#ifndef SV_SWEEP_REVWARP
+#define SV_SWEEP_REVWARP 1
+#endif
 #ifndef SV_SWEEP_UNCOND
 #define SV_SWEEP_UNCOND 1
 #endif
@@ -73,7 +82,8 @@ struct SweepGeom {
   static constexpr int WTA = SECOND ? VEC : 0;    // per worker: final S of one pixel (neighbour lookup)
   static constexpr int OFF_RING = RW * ROWBUF;    // in-warp rings of workers 1..RW-1, then the ring of worker 0
   static constexpr int OFF_RING0 = OFF_RING + (RW - 1) * kRingI * ENT;
-  static constexpr int OFF_WTA = OFF_RING0 + kRingX * ENT;
+  static constexpr int OFF_XOUT = OFF_RING0 + kRingX * ENT;  // export of the last worker when it does not go to a ring
+  static constexpr int OFF_WTA = OFF_XOUT + ENT;
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
   static constexpr int STAGE_U4 = 2 * ENT;         // one flag-in-data entry being fetched from the left CTA
   static constexpr int NW_FIT = (kSmemMax - kFlagBytes - STAGE_U4 * 16) / (WARP_U4 * 16);
@@ -128,6 +138,23 @@ __device__ __forceinline__ void st_edge(uint4* p, const uint4& v, uint32_t tag) 
 __device__ __forceinline__ void cp_async16(uint4* smemDst, const uint4* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
 }
+// bulk (TMA) copy global -> shared whose completion is signalled on an mbarrier: unlike cp.async + wait_all, waiting
+// for it does not also wait for the warp's other outstanding global loads (the C / S prefetch of the next chunk)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long now_ns() {
@@ -160,13 +187,21 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
   constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
   extern __shared__ uint4 smem[];
   uint4* stage = smem + NW * G::WARP_U4;
-  int* flags = (int*)(stage + G::STAGE_U4);
+  uint64_t* sBar = (uint64_t*)(stage + G::STAGE_U4);  // completion of the bulk copy into `stage`
+  int* flags = (int*)(sBar + 2);
   int* sProg = flags;            // [NW] rows exported by the last worker of warp w (last row + 1)
   int* sCons = flags + NW;       // [NW] rows finished by the first worker of warp w (next row)
   int* sTicket = flags + 2 * NW;
   volatile int* sAbort = flags + 2 * NW + 1;
 
+  // position of this warp in the CTA's chain of strips.  The scheduler arbitrates hardware warps highest id first, and
+  // a chain runs at the pace of its head (the warp that imports from the left CTA and never finds slack), so the head
+  // is the hardware warp with the highest id and followers fill the issue slots it leaves.
+#if SV_SWEEP_REVWARP
+  const int warp = NW - 1 - (threadIdx.x >> 5), lane = threadIdx.x & 31;
+#else
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
   const int j = lane / LPP, gl = lane % LPP;
   const int W1 = a.W1, H = a.H;
   const bool active = gl < a.nAct;           // lane holds disparities
@@ -176,7 +211,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
 
   // shared memory starts out as valid (zero) path costs: stale entries are read under an override only
   for (int i = threadIdx.x; i < NW * G::WARP_U4; i += blockDim.x) smem[i] = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) *sAbort = 0;
+  if (threadIdx.x == 0) { *sAbort = 0; mbar_init(sBar, 1); }
+  int barPhase = 0;  // parity of the next completion of sBar (only warp 0 uses it)
 
   uint4* wbase = smem + warp * G::WARP_U4;
   uint4* rowbuf = wbase + j * G::ROWBUF + gl;  // lane-private: [pixel][path][half][gl]
@@ -187,6 +223,15 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
   uint4* ring0 = wbase + G::OFF_RING0;
   uint16_t* wta = (uint16_t*)(wbase + G::OFF_WTA + j * G::WTA);
 
+#if SV_SWEEP_PROF
+  long long pfTask = 0, pfLeft = 0, pfRight = 0, pfGlobal = 0, pfIdle = 0, pfSteps = 0, pfA = 0, pfBlock = 0, pfFail = 0, pfB = 0, pfA1 = 0, pfA3 = 0, pfA5 = 0;
+  long long pfT0 = clock64();
+#define PF_BEGIN long long pf_t = clock64()
+#define PF_END(acc) acc += clock64() - pf_t
+#else
+#define PF_BEGIN
+#define PF_END(acc)
+#endif
   const int ntasks = a.nframes * a.G;
   for (;;) {
     __syncthreads();
@@ -201,6 +246,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
     if (lane == 0) { sProg[warp] = 0; sCons[warp] = y0of(sFirst); }
     __syncthreads();
     if (sFirst > a.smax) continue;  // whole warp beyond the last strip (still takes part in the barriers above)
+#if SV_SWEEP_PROF
+    pfIdle += clock64() - pfT0;
+    const long long pfStart = clock64();
+#endif
 
     const int s = sFirst + j;
     const int y0 = y0of(s), y1 = y1of(s);            // rows of this strip (empty when s > smax)
@@ -244,11 +293,20 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
       constexpr int NIT = (ENT + 31) / 32;
       uint4 d[NIT];
       bool good = true;
+      // explicit shared-memory accesses: through generic pointers these would be generic loads / stores
+      const uint32_t ssrc = fromGlobal ? 0u : (uint32_t)__cvta_generic_to_shared(src);
+      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst);
 #pragma unroll
       for (int it = 0; it < NIT; it++) {
         const int q = lane + 32 * it;
         if (q < ENT) {
-          const uint4 u = fromGlobal ? ld_edge(src + 2 * q) : src[2 * q], v = fromGlobal ? ld_edge(src + 2 * q + 1) : src[2 * q + 1];
+          uint4 u, v;
+          if (fromGlobal) {
+            u = ld_edge(src + 2 * q); v = ld_edge(src + 2 * q + 1);
+          } else {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ssrc + 32 * q) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ssrc + 32 * q + 16) : "memory");
+          }
           good = good && u.y == a.tag && u.w == a.tag && v.y == a.tag && v.w == a.tag;
           d[it] = make_uint4(u.x, u.z, v.x, v.z);
         }
@@ -258,7 +316,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
           const int q = lane + 32 * it;
-          if (q < ENT) dst[q] = d[it];
+          if (q < ENT)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdst + 16 * q), "r"(d[it].x), "r"(d[it].y), "r"(d[it].z), "r"(d[it].w) : "memory");
         }
       }
       return good;
@@ -275,20 +334,42 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
       const int rL = T - (RW - 1);
       const bool actL = rL >= y0L && rL <= y1L;          // worker RW-1 has a row (and a strip)
       // ================================================================== phase A: hand-over in
+#if SV_SWEEP_PROF
+      const long long pfA0 = clock64();
+#endif
       if (hasLeft && act0) {
         const int need = min(T, y1p) + 1;
         where = leftGlobal ? 3 : 1;
         if (!leftGlobal) {
-          ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status);
+          { PF_BEGIN; ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status); PF_END(pfLeft); }
         } else {
           // 1. the entry requested in the previous step has had a whole step to arrive in `stage`
+#if SV_SWEEP_PROF
+          const long long pfq1 = clock64();
+#endif
           if (pendRow >= 0) {
+#if SV_SWEEP_BULK
+            for (int n = 0; !mbar_try_wait(sBar, barPhase);)
+              if (((++n) & 255) == 0 && *sAbort) { ok = false; break; }
+            barPhase ^= 1;
+#else
             cp_async_wait_all();
             __syncwarp();
+#endif
             if (pendRow == loaded && take_entry(stage, ring0 + (pendRow & (kRingX - 1)) * ENT, false)) loaded++;
+#if SV_SWEEP_PROF
+            else pfFail++;
+#endif
             pendRow = -1;
           }
+#if SV_SWEEP_PROF
+          pfA1 += clock64() - pfq1;
+#endif
           // 2. rows needed now: fetch them directly, polling until the left CTA has written them
+          PF_BEGIN;
+#if SV_SWEEP_PROF
+          if (loaded < need) pfBlock++;
+#endif
           int n = 0;
           unsigned long long t0 = 0;
           while (loaded < need) {
@@ -300,16 +381,31 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
               if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
             }
           }
+          PF_END(pfGlobal);
           // 3. request the next row (entries T-1 and T are in use, so rows up to T+2 have a free slot)
+#if SV_SWEEP_PROF
+          const long long pfq3 = clock64();
+#endif
           if (ok && loaded <= min(T + 2, y1p)) {
             const uint4* src = gin + (size_t)loaded * (2 * ENT);
+#if SV_SWEEP_BULK
+            __syncwarp();  // every lane is done reading `stage`
+            if (lane == 0) bulk_load(stage, src, 2 * ENT * 16, sBar);
+#else
             for (int q = lane; q < 2 * ENT; q += 32) cp_async16(stage + q, src + q);
+#endif
             pendRow = loaded;
           }
+#if SV_SWEEP_PROF
+          pfA3 += clock64() - pfq3;
+#endif
         }
       }
-      if (hasRight && actL && !rightGlobal && ok) { where = 2; ok = wait_cta(&sCons[warp + 1], rL - 3, sAbort, a.status); }
+      if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - 3, sAbort, a.status); PF_END(pfRight); }
       if (!ok) break;
+#if SV_SWEEP_PROF
+      const long long pfq5 = clock64();
+#endif
       where = 0;
       __syncwarp();
       {
@@ -330,16 +426,23 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
       }
       __syncwarp();
       if (act0 && lane == 0) st_flag(&sCons[warp], T);  // rows < T are done with: their entries may be overwritten
+#if SV_SWEEP_PROF
+      pfA5 += clock64() - pfq5;
+      pfA += clock64() - pfA0;
+      const long long pfB0 = clock64();
+#endif
       // ================================================================== phase B: kK pixels
       const int yp = a.flip ? H - 1 - r : r;
       const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
       const bool actn = (r + 1) >= y0 && (r + 1) <= y1;
       const bool top = r == 0;
-      uint4* eOut = outRing + (r & outMask) * ENT + gl;
-      const bool expRing = (j < RW - 1) || (hasRight && act && !rightGlobal);
+      // export target of this chunk: the ring of the right neighbour, or (no neighbour / inactive row / neighbour in
+      // another CTA) a private entry that the last warp copies to global memory after the chunk
+      const bool toRing = (j < RW - 1) || (hasRight && act && !rightGlobal);
       const bool expGlobal = (j == RW - 1) && rightGlobal && act;
-      uint4* gOut = expGlobal ? gout + (size_t)r * (2 * ENT) + 2 * gl : nullptr;
+      uint4* eOut = (toRing ? outRing + (r & outMask) * ENT : wbase + G::OFF_XOUT) + gl;
       uint32_t mDLprev = 0;
+      uint4 eMins = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int i = 0; i < kK; i++) {
         const int x = xl + i;
@@ -417,39 +520,17 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
         recM[i][0] = mV; recM[i][1] = mDL; recM[i][2] = mDR;
         // ---- hand-over to the right neighbour: the last two pixels of the chunk
         if (i >= kK - 2) {
-          if (expRing) {
 #pragma unroll
-            for (int h = 0; h < NV; h++) {
-              if (i == kK - 2) {
-                if (HAS_DL) eOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
-              } else {
-                eOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
-                if (HAS_V) eOut[1 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
-                if (HAS_DL) eOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
-              }
-            }
-            if (i == kK - 1 && gl == 0) (eOut - gl)[4 * VEC] = make_uint4(mH, mV, mDL, mDLprev);
-          } else if (expGlobal) {
-#pragma unroll
-            for (int h = 0; h < NV; h++) {
-              if (i == kK - 2) {
-                if (HAS_DL) st_edge(gOut + 2 * (3 * VEC + h * LPP), make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]), a.tag);
-              } else {
-                st_edge(gOut + 2 * (0 * VEC + h * LPP), make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]), a.tag);
-                if (HAS_V) st_edge(gOut + 2 * (1 * VEC + h * LPP), make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]), a.tag);
-                if (HAS_DL) st_edge(gOut + 2 * (2 * VEC + h * LPP), make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]), a.tag);
-              }
-            }
-            if (i == kK - 1 && gl == 0) st_edge(gOut - 2 * gl + 2 * (4 * VEC), make_uint4(mH, mV, mDL, mDLprev), a.tag);
-            // paths this mode does not carry still need their tag: the reader validates the whole entry
-            if (i == kK - 1) {
-#pragma unroll
-              for (int h = 0; h < NV; h++) {
-                if (!HAS_V) st_edge(gOut + 2 * (1 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag);
-                if (!HAS_DL) { st_edge(gOut + 2 * (2 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag); st_edge(gOut + 2 * (3 * VEC + h * LPP), make_uint4(0, 0, 0, 0), a.tag); }
-              }
+          for (int h = 0; h < NV; h++) {
+            if (i == kK - 2) {
+              if (HAS_DL) eOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
+            } else {
+              eOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
+              if (HAS_V) eOut[1 * VEC + h * LPP] = make_uint4(Vd1[4 * h], Vd1[4 * h + 1], Vd1[4 * h + 2], Vd1[4 * h + 3]);
+              if (HAS_DL) eOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
             }
           }
+          if (i == kK - 1) eMins = make_uint4(mH, mV, mDL, mDLprev);
           mDLprev = mDL;
         }
         // ---- output of the pixel
@@ -477,14 +558,33 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
         }
         mDLd2 = mDLd1; mDLd1 = omDL; mVd1 = omV;
       }
+#if SV_SWEEP_PROF
+      pfB += clock64() - pfB0;
+#endif
       // ================================================================== hand-over out
+      if (gl == 0) (eOut - gl)[4 * VEC] = eMins;
+      if (expGlobal) {  // the right neighbour is in another CTA: flag-in-data copy of this lane's part of the entry
+        uint4* gOut = gout + (size_t)r * (2 * ENT) + 2 * gl;
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+#pragma unroll
+          for (int h = 0; h < NV; h++) st_edge(gOut + 2 * (v * VEC + h * LPP), eOut[v * VEC + h * LPP], a.tag);
+        if (gl == 0) st_edge(gOut + 2 * (4 * VEC), eMins, a.tag);
+      }
       __syncwarp();
       if (lane == 0 && actL && hasRight && !rightGlobal) st_flag(&sProg[warp], rL + 1);
     }
+#if SV_SWEEP_PROF
+    pfTask += clock64() - pfStart; pfSteps += Tend - Tbeg + 1; pfT0 = clock64();
+#endif
     if (!ok && lane == 0)
       printf("svgpu sweep: cta %d warp %d task (frame %d, group %d) stopped at row step %d of [%d,%d] while waiting for %s\n", blockIdx.x, warp, frame, sg,
              Tlast, Tbeg, Tend, where == 1 ? "left warp" : where == 2 ? "right warp" : where == 3 ? "left CTA" : "nothing");
   }
+#if SV_SWEEP_PROF
+  pfIdle += clock64() - pfT0;
+  if (lane == 0) printf("PF %d %d %d %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", (int)SECOND, blockIdx.x, warp, pfTask, pfLeft, pfRight, pfGlobal, pfIdle, pfSteps, pfA, pfB, pfBlock, pfFail, pfA1, pfA3, pfA5);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
