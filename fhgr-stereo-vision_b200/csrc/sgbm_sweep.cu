@@ -20,8 +20,9 @@
 //     chunk and the vertical/diagonal paths of the two pixels above-left of it, and hands the same to its
 //     right neighbour: one small "entry" per row instead of one hand-over per pixel;
 //   * a warp holds 32/LPP neighbouring strips in lock step, one row apart (entries through shared memory,
-//     __syncwarp only); warps of a CTA hand over through shared-memory rings with acquire/release
-//     counters; CTAs hand over through a global edge buffer + progress counter;
+//     __syncwarp only); warps of a CTA hand over through shared-memory rings with volatile counters; CTAs hand over
+//     through a global edge buffer whose row count is published after a fence every few rows, the entries being
+//     copied straight into the consumer's ring by the TMA one row ahead of their use;
 //   * CTAs are persistent and draw (frame, strip group) tasks from a ticket counter, strip groups in
 //     ascending order.  A task only waits for the task to its left, which has a smaller ticket and is
 //     therefore resident or finished: no deadlock whatever the residency.
@@ -30,7 +31,6 @@
 // group interleaved (word i of a group = disparities d0+i and d0+i+8), so that the d-1 / d+1 neighbours of
 // a packed register are simply the previous / next register of the lane (sgbm_device.cuh).
 #include <algorithm>
-#include <atomic>
 
 #include "common.cuh"
 #include "sgbm_device.cuh"
@@ -52,11 +52,11 @@ namespace {
 #ifndef SV_SWEEP_PROF
 #define SV_SWEEP_PROF 0
 #endif
-#ifndef SV_SWEEP_BULK
-#define SV_SWEEP_BULK 1
-#endif
 #ifndef SV_SWEEP_REVWARP
 #define SV_SWEEP_REVWARP 1
+#endif
+#ifndef SV_SWEEP_PUBLISH
+#define SV_SWEEP_PUBLISH 4   // rows between two publications (fence + counter) of the CTA-crossing entries
 #endif
 #ifndef SV_SWEEP_UNCOND
 #define SV_SWEEP_UNCOND 1
@@ -85,7 +85,7 @@ struct SweepGeom {
   static constexpr int OFF_XOUT = OFF_RING0 + kRingX * ENT;  // export of the last worker when it does not go to a ring
   static constexpr int OFF_WTA = OFF_XOUT + ENT;
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
-  static constexpr int STAGE_U4 = 2 * ENT;         // one flag-in-data entry being fetched from the left CTA
+  static constexpr int STAGE_U4 = 1;               // the mbarrier of the TMA copies from the left CTA's entries
   static constexpr int NW_FIT = (kSmemMax - kFlagBytes - STAGE_U4 * 16) / (WARP_U4 * 16);
   static constexpr int NW = NW_FIT > kMaxNW ? kMaxNW : NW_FIT;  // warps per CTA
   static constexpr int SPC = NW * RW;             // strips per CTA task
@@ -96,8 +96,8 @@ struct SweepArgs {
   const uint4* C;
   uint4* S;
   uint2* sel;     // [frame][H][W1]  pass 2: {reject<<31 | minS<<16 | best, S[best-1]<<16 | S[best+1]}
-  uint4* edges;   // [frame][G-1][H][2*ENT]  flag-in-data entries (see st_edge)
-  uint32_t tag;   // launch tag of the entries of this launch
+  uint4* edges;   // [frame][G-1][H][ENT]  hand-over entries between CTAs
+  int* gprog;     // [frame][G]  rows of a strip group's last strip that are visible in `edges`
   int* ticket;
   int* status;
   int W1, H, D, nAct;          // nAct = D/16 lanes of a worker hold disparities
@@ -123,23 +123,18 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 __device__ __forceinline__ void st_flag(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-// Entries that cross a CTA boundary travel through global memory in "flag in data" form: every 16-byte store
-// carries two payload words and two copies of the launch tag, so the reader can tell a complete entry from a
-// stale or half-written one without any fence or separate flag.
-__device__ __forceinline__ uint4 ld_edge(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_edge(uint4* p, const uint4& v, uint32_t tag) {  // p -> two uint4 of the LL entry
-  __stcg(p, make_uint4(v.x, tag, v.y, tag));
-  __stcg(p + 1, make_uint4(v.z, tag, v.w, tag));
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
-__device__ __forceinline__ void cp_async16(uint4* smemDst, const uint4* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
-}
-// bulk (TMA) copy global -> shared whose completion is signalled on an mbarrier: unlike cp.async + wait_all, waiting
-// for it does not also wait for the warp's other outstanding global loads (the C / S prefetch of the next chunk)
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// bulk (TMA) copy global -> shared whose completion is signalled on an mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -155,7 +150,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity) {
                : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long now_ns() {
   unsigned long long t;
@@ -186,9 +180,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
   constexpr bool HAS_V = (PATHS & P_V) != 0, HAS_DL = (PATHS & P_DL) != 0, HAS_DR = (PATHS & P_DR) != 0;
   constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
   extern __shared__ uint4 smem[];
-  uint4* stage = smem + NW * G::WARP_U4;
-  uint64_t* sBar = (uint64_t*)(stage + G::STAGE_U4);  // completion of the bulk copy into `stage`
-  int* flags = (int*)(sBar + 2);
+  uint64_t* sBar = (uint64_t*)(smem + NW * G::WARP_U4);  // completion of the TMA copy of a CTA-crossing entry
+  int* flags = (int*)(smem + NW * G::WARP_U4 + G::STAGE_U4);
   int* sProg = flags;            // [NW] rows exported by the last worker of warp w (last row + 1)
   int* sCons = flags + NW;       // [NW] rows finished by the first worker of warp w (next row)
   int* sTicket = flags + 2 * NW;
@@ -268,10 +261,13 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
     uint4* Sf = a.S + (size_t)frame * a.frameU4 + glc * NV;
     const uint4* gin = nullptr;
     uint4* gout = nullptr;
-    if (leftGlobal) gin = a.edges + ((size_t)frame * (a.G - 1) + (sg - 1)) * (size_t)H * (2 * ENT);
-    if (rightGlobal) gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * (2 * ENT);
+    const int* gflagIn = nullptr;
+    int* gflagOut = nullptr;
+    if (leftGlobal) { gin = a.edges + ((size_t)frame * (a.G - 1) + (sg - 1)) * (size_t)H * ENT; gflagIn = a.gprog + frame * a.G + (sg - 1); }
+    if (rightGlobal) { gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * ENT; gflagOut = a.gprog + frame * a.G + sg; }
+    int gseen = 0, gpend = 0;   // rows the left CTA has published (cached / polled one step ahead)
     int loaded = max(y0F - 1, 0);  // rows [.., loaded) of the left CTA's entries are in ring0
-    int pendRow = -1;              // row whose entry is on its way into `stage`
+    int pendRow = -1;              // row whose entry the TMA is copying into ring0
 
     // ---- per-task register state
     uint32_t Hs[kNR], Vd1[kNR], DLd1[kNR], DLd2[kNR];
@@ -286,42 +282,6 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
 #pragma unroll
       for (int h = 0; h < NV; h++) cb[i][h] = sb[i][h] = make_uint4(0, 0, 0, 0);
     }
-
-    // moves one flag-in-data entry (global memory or `stage`) into a ring slot if every piece carries this
-    // launch's tag; all lanes of the warp call it, the result is warp-uniform
-    auto take_entry = [&](const uint4* src, uint4* dst, bool fromGlobal) -> bool {
-      constexpr int NIT = (ENT + 31) / 32;
-      uint4 d[NIT];
-      bool good = true;
-      // explicit shared-memory accesses: through generic pointers these would be generic loads / stores
-      const uint32_t ssrc = fromGlobal ? 0u : (uint32_t)__cvta_generic_to_shared(src);
-      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst);
-#pragma unroll
-      for (int it = 0; it < NIT; it++) {
-        const int q = lane + 32 * it;
-        if (q < ENT) {
-          uint4 u, v;
-          if (fromGlobal) {
-            u = ld_edge(src + 2 * q); v = ld_edge(src + 2 * q + 1);
-          } else {
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ssrc + 32 * q) : "memory");
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ssrc + 32 * q + 16) : "memory");
-          }
-          good = good && u.y == a.tag && u.w == a.tag && v.y == a.tag && v.w == a.tag;
-          d[it] = make_uint4(u.x, u.z, v.x, v.z);
-        }
-      }
-      good = __all_sync(0xFFFFFFFFu, good);
-      if (good) {
-#pragma unroll
-        for (int it = 0; it < NIT; it++) {
-          const int q = lane + 32 * it;
-          if (q < ENT)
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdst + 16 * q), "r"(d[it].x), "r"(d[it].y), "r"(d[it].z), "r"(d[it].w) : "memory");
-        }
-      }
-      return good;
-    };
 
     bool ok = true;
     int where = 0, Tlast = 0;
@@ -343,62 +303,55 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
         if (!leftGlobal) {
           { PF_BEGIN; ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status); PF_END(pfLeft); }
         } else {
-          // 1. the entry requested in the previous step has had a whole step to arrive in `stage`
-#if SV_SWEEP_PROF
-          const long long pfq1 = clock64();
-#endif
+          // The left CTA publishes a row count after a fence every few rows; published entries are copied straight into
+          // this warp's ring by the TMA, one row ahead of their use.
+          // 1. the entry requested in the previous step has had a whole step to arrive
           if (pendRow >= 0) {
-#if SV_SWEEP_BULK
             for (int n = 0; !mbar_try_wait(sBar, barPhase);)
               if (((++n) & 255) == 0 && *sAbort) { ok = false; break; }
             barPhase ^= 1;
-#else
-            cp_async_wait_all();
-            __syncwarp();
-#endif
-            if (pendRow == loaded && take_entry(stage, ring0 + (pendRow & (kRingX - 1)) * ENT, false)) loaded++;
-#if SV_SWEEP_PROF
-            else pfFail++;
-#endif
+            loaded = pendRow + 1;
             pendRow = -1;
           }
-#if SV_SWEEP_PROF
-          pfA1 += clock64() - pfq1;
-#endif
-          // 2. rows needed now: fetch them directly, polling until the left CTA has written them
+          // 2. rows needed now
           PF_BEGIN;
-#if SV_SWEEP_PROF
-          if (loaded < need) pfBlock++;
-#endif
           int n = 0;
           unsigned long long t0 = 0;
-          while (loaded < need) {
-            if (take_entry(gin + (size_t)loaded * (2 * ENT), ring0 + (loaded & (kRingX - 1)) * ENT, true)) { loaded++; continue; }
-            __nanosleep(200);
-            if (((++n) & 63) == 0) {
-              if (!t0) t0 = now_ns();
-              if (*sAbort) { ok = false; break; }
-              if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
+          while (loaded < need && ok) {
+            if (gseen <= loaded) {
+              gseen = ld_acquire_gpu(gflagIn);
+              if (gseen <= loaded) {
+                __nanosleep(200);
+                if (((++n) & 63) == 0) {
+                  if (!t0) t0 = now_ns();
+                  if (*sAbort) { ok = false; break; }
+                  if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
+                }
+                continue;
+              }
             }
+            __syncwarp();
+            if (lane == 0) bulk_load(ring0 + (loaded & (kRingX - 1)) * ENT, gin + (size_t)loaded * ENT, ENT * 16, sBar);
+            for (int m = 0; !mbar_try_wait(sBar, barPhase);)
+              if (((++m) & 255) == 0 && *sAbort) { ok = false; break; }
+            barPhase ^= 1;
+            loaded++;
           }
           PF_END(pfGlobal);
           // 3. request the next row (entries T-1 and T are in use, so rows up to T+2 have a free slot)
-#if SV_SWEEP_PROF
-          const long long pfq3 = clock64();
-#endif
           if (ok && loaded <= min(T + 2, y1p)) {
-            const uint4* src = gin + (size_t)loaded * (2 * ENT);
-#if SV_SWEEP_BULK
-            __syncwarp();  // every lane is done reading `stage`
-            if (lane == 0) bulk_load(stage, src, 2 * ENT * 16, sBar);
-#else
-            for (int q = lane; q < 2 * ENT; q += 32) cp_async16(stage + q, src + q);
-#endif
-            pendRow = loaded;
+            if (gseen <= loaded) {
+              // the count is polled with a relaxed load one step ahead (no stall); only when that hint says new rows
+              // are there is it confirmed with an acquire load, which orders the copy below behind the publication
+              if (gpend > loaded) gseen = ld_acquire_gpu(gflagIn);
+              else gpend = ld_relaxed_gpu(gflagIn);
+            }
+            if (gseen > loaded) {
+              __syncwarp();
+              if (lane == 0) bulk_load(ring0 + (loaded & (kRingX - 1)) * ENT, gin + (size_t)loaded * ENT, ENT * 16, sBar);
+              pendRow = loaded;
+            }
           }
-#if SV_SWEEP_PROF
-          pfA3 += clock64() - pfq3;
-#endif
         }
       }
       if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - 3, sAbort, a.status); PF_END(pfRight); }
@@ -563,13 +516,20 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
 #endif
       // ================================================================== hand-over out
       if (gl == 0) (eOut - gl)[4 * VEC] = eMins;
-      if (expGlobal) {  // the right neighbour is in another CTA: flag-in-data copy of this lane's part of the entry
-        uint4* gOut = gout + (size_t)r * (2 * ENT) + 2 * gl;
+      if (expGlobal) {  // the right neighbour is in another CTA: copy this lane's part of the entry to global memory
+        uint4* gOut = gout + (size_t)r * ENT + gl;
 #pragma unroll
         for (int v = 0; v < 4; v++)
 #pragma unroll
-          for (int h = 0; h < NV; h++) st_edge(gOut + 2 * (v * VEC + h * LPP), eOut[v * VEC + h * LPP], a.tag);
-        if (gl == 0) st_edge(gOut + 2 * (4 * VEC), eMins, a.tag);
+          for (int h = 0; h < NV; h++) __stcg(gOut + v * VEC + h * LPP, eOut[v * VEC + h * LPP]);
+        if (gl == 0) __stcg(gOut - gl + 4 * VEC, eMins);
+      }
+      if (rightGlobal && actL && (((rL - y0L) % SV_SWEEP_PUBLISH) == SV_SWEEP_PUBLISH - 1 || rL == y1L)) {
+        // publish: the fence makes the entries written so far visible before the counter (it also waits for this warp's
+        // outstanding prefetch loads, which is why it is not done for every row)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_relaxed_gpu(gflagOut, rL + 1);
       }
       __syncwarp();
       if (lane == 0 && actL && hasRight && !rightGlobal) st_flag(&sProg[warp], rL + 1);
@@ -639,18 +599,20 @@ cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, int grid, cud
 
 }  // namespace
 
-size_t sgbm_flags_bytes(const SgbmCfg&, int) { return 256; }  // the ticket counter
+size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
+  if (cfg.W1 <= 0) return 256;
+  return ((size_t)nframes * std::max(groups_of(cfg, false), groups_of(cfg, true)) + 64) * sizeof(int);
+}
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
   const int g = std::max(groups_of(cfg, false), groups_of(cfg, true));
-  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * 2 * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
+  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
 }
 
 // Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats) {
   static int numSM = 0;
-  static std::atomic<uint32_t> launchTag{0};
   if (!numSM) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -660,6 +622,7 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.C = (const uint4*)sc.C; a.S = (uint4*)sc.S; a.sel = (uint2*)sc.sel;
   a.edges = (uint4*)sc.edges;
   a.ticket = (int*)sc.flags;
+  a.gprog = (int*)sc.flags + 64;
   a.status = sc.status;
   a.W1 = cfg.W1; a.H = cfg.H; a.D = cfg.D; a.nAct = cfg.D / kDPL;
   a.nframes = nframes; a.smax = smax_of(cfg); a.debugS = debugS;
@@ -676,9 +639,7 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   const int lpp = lpp_of(cfg.D);
   for (int pass = 0; pass < 2; pass++) {
     a.G = groups_of(cfg, pass == 1);
-    a.tag = ++launchTag;  // 0 is never used: the edge buffer starts out zeroed
-    if (a.tag == 0) a.tag = ++launchTag;
-    cudaError_t e = cudaMemsetAsync(sc.flags, 0, 256, st);
+    cudaError_t e = cudaMemsetAsync(sc.flags, 0, ((size_t)nframes * a.G + 64) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     a.flip = pass;
     const int paths = pass ? pass2 : pass1;
