@@ -272,3 +272,41 @@ def test_cpp_facade_matches_python_pipeline(svgpu, oracle, tmp_path):
     for key, p in (("p0", p0), ("p1", p1)):
         want = full["xyz"][p[0], p[1]]
         assert np.allclose(np.array(got[key].split(), np.float32), want, rtol=1e-6, atol=0), (key, got[key], want)
+
+
+def test_sgbm_random_configs_bit_exact(svgpu, oracle):
+    """Seeded random sweep over image sizes (incl. fewer computed columns than one strip and single-row images),
+    disparity ranges, block sizes, penalties, uniqueness ratios, minDisparity signs and all three modes, on textured
+    and on saturating noise inputs: bit-exact against the oracle."""
+    from svgpu.synth import synth_pair
+    rng = np.random.default_rng(20261018)
+    bad = []
+    for case in range(48):
+        D = int(rng.choice([16, 32, 48, 64, 80, 96, 128, 160, 224, 256]))
+        minD = int(rng.choice([0, 0, 0, 3, -5, 16, -16]))
+        bs = int(rng.choice([1, 3, 5, 7, 9, 11]))
+        mode = int(rng.choice([0, 1, 3]))
+        W1 = int(rng.choice([1, 2, 3, 5, 17, 40, 97, 150, 260]))
+        W = max(minD + D, 0) - min(minD, 0) + W1
+        H = int(rng.choice([1, 2, 5, 9, 33, 70]))
+        if mode != 3 and W - (minD + D) <= bs // 2:  # the reference raises for this combination (tested elsewhere)
+            W += bs // 2 + 1
+        cap = int(rng.choice([1, 15, 31, 32, 63]))
+        P1 = int(rng.integers(1, 400))
+        P2 = P1 + int(rng.integers(1, 1200))
+        prm = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=int(rng.choice([-1, 0, 1, 4])),
+                   preFilterCap=cap, uniquenessRatio=int(rng.choice([0, 5, 15, 40, 100])), speckleWindowSize=0, speckleRange=0, mode=mode)
+        if bs * bs * (2 * (max(cap, 15) | 1) + 63) + P2 > 32767:
+            continue  # outside the 16-bit contract (rejected by svgpu_set_sgbm, as by this implementation's header)
+        if rng.random() < 0.3:
+            l = rng.integers(0, 256, (H, W), dtype=np.uint8)
+            r = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        else:
+            l, r = synth_pair(H, W, max(min(D, W // 2), 1), seed=case)
+        want = oracle.sgbm(l, r, **prm)
+        with svgpu.Context(W, H) as ctx:
+            ctx.set_sgbm(**prm)
+            got = ctx.sgbm(l, r)
+        if nmismatch(got, want):
+            bad.append((case, H, W, prm, nmismatch(got, want)))
+    assert not bad, bad
