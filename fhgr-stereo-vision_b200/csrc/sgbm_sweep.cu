@@ -612,12 +612,10 @@ size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
 // Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats) {
-  static int numSM = 0;
-  if (!numSM) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int dev = 0, numSM = 0;
+  cudaError_t e0 = cudaGetDevice(&dev);
+  if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);
+  if (e0 != cudaSuccess) return e0;
   SweepArgs a{};
   a.C = (const uint4*)sc.C; a.S = (uint4*)sc.S; a.sel = (uint2*)sc.sel;
   a.edges = (uint4*)sc.edges;
