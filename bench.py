@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="svgpu", choices=["svgpu", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("SVGPU_BENCH_BATCH", 32)), help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SVGPU_BENCH_BATCH", 64)), help="pairs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "svgpu" else args.warmup
