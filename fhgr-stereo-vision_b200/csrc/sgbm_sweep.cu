@@ -64,7 +64,7 @@ namespace {
 constexpr int kK = SV_SWEEP_K;  // strip width = pixels per chunk
 constexpr int kRingX = 4;      // entries in the import ring of a warp's first worker (fed by another warp / CTA)
 constexpr int kRingI = 2;      // entries in the import ring of the other workers (fed in lock step by the same warp)
-constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a hand-over that takes longer than this aborts the kernel
+constexpr unsigned long long kWaitLimitNs = 10000000000ull;  // a hand-over that takes longer than this aborts the kernel
 constexpr int kFlagBytes = 256;   // hand-over counters, ticket and abort flag at the end of shared memory
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kMaxNW = SV_SWEEP_MAXNW;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
