@@ -61,8 +61,20 @@ namespace {
 #ifndef SV_SWEEP_UNCOND
 #define SV_SWEEP_UNCOND 1
 #endif
+#ifndef SV_SWEEP_FAKE
+#define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
+#endif
 constexpr int kK = SV_SWEEP_K;  // strip width = pixels per chunk
-constexpr int kRingX = 4;      // entries in the import ring of a warp's first worker (fed by another warp / CTA)
+#ifndef SV_SWEEP_RINGX
+#define SV_SWEEP_RINGX 8
+#endif
+constexpr int kRingX = SV_SWEEP_RINGX;  // entries in the import ring of a warp's first worker (fed by another warp / CTA)
+#ifndef SV_SWEEP_AHEAD
+#define SV_SWEEP_AHEAD (SV_SWEEP_RINGX - 1)
+#endif
+constexpr int kPub = SV_SWEEP_PUBLISH;
+constexpr int kAhead = SV_SWEEP_AHEAD;  // rows a warp may run ahead of the warp that consumes its entries (< kRingX)
+static_assert(kRingX % kPub == 0 && kRingX >= kPub + 2, "import blocks must tile the ring and leave room for the two entries in use");
 constexpr int kRingI = 2;      // entries in the import ring of the other workers (fed in lock step by the same warp)
 constexpr unsigned long long kWaitLimitNs = 10000000000ull;  // a hand-over that takes longer than this aborts the kernel
 constexpr int kFlagBytes = 256;   // hand-over counters, ticket and abort flag at the end of shared memory
@@ -143,6 +155,12 @@ __device__ __forceinline__ void bulk_load(void* smemDst, const void* gsrc, uint3
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(b), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    (uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, int parity) {  // never suspends
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity) {
   uint32_t ok;
@@ -248,7 +266,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
     const int y0 = y0of(s), y1 = y1of(s);            // rows of this strip (empty when s > smax)
     const int jLast = min(RW - 1, a.smax - sFirst);  // last worker with a strip
     const int sLast = sFirst + RW - 1;
-    const bool hasLeft = sFirst > 0, hasRight = sLast < a.smax;
+    const bool hasLeft = sFirst > 0 && !((SV_SWEEP_FAKE & 1) && warp == 0), hasRight = sLast < a.smax && !((SV_SWEEP_FAKE & 2) && warp == NW - 1);
     const int y0F = y0of(sFirst), y1F = y1of(sFirst);
     const int y0L = y0of(sLast), y1L = y1of(sLast);
     const int y0p = hasLeft ? y0of(sFirst - 1) : 0;   // rows of the strip left of worker 0: its entry k is row y0p + k
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
     if (rightGlobal) { gout = a.edges + ((size_t)frame * (a.G - 1) + sg) * (size_t)H * ENT; gflagOut = a.gprog + frame * a.G + sg; }
     int gseen = 0, gpend = 0;   // rows the left CTA has published (cached / polled one step ahead)
     int loaded = max(y0F - 1, 0);  // rows [.., loaded) of the left CTA's entries are in ring0
-    int pendRow = -1;              // row whose entry the TMA is copying into ring0
+    int pendEnd = 0;               // rows [loaded, pendEnd) are being copied into ring0 by the TMA
 
     // ---- per-task register state
     uint32_t Hs[kNR], Vd1[kNR], DLd1[kNR], DLd2[kNR];
@@ -303,58 +321,63 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
         if (!leftGlobal) {
           { PF_BEGIN; ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status); PF_END(pfLeft); }
         } else {
-          // The left CTA publishes a row count after a fence every few rows; published entries are copied straight into
-          // this warp's ring by the TMA, one row ahead of their use.
-          // 1. the entry requested in the previous step has had a whole step to arrive
-          if (pendRow >= 0) {
+          // The left CTA publishes a row count after a fence every kPub rows; published entries are copied straight into
+          // this warp's ring by the TMA in blocks of up to kPub rows (row-aligned like the publications), ahead of use.
+          auto blockEnd = [&](int from) { return min((from / kPub) * kPub + kPub, y1p + 1); };
+          auto issue = [&](int from, int to) {
+            __syncwarp();
+            if (lane == 0) bulk_load(ring0 + (from & (kRingX - 1)) * ENT, gin + (size_t)from * ENT, (uint32_t)(to - from) * (ENT * 16), sBar);
+          };
+          auto finish = [&]() {  // wait for the block in flight
             for (int n = 0; !mbar_try_wait(sBar, barPhase);)
               if (((++n) & 255) == 0 && *sAbort) { ok = false; break; }
             barPhase ^= 1;
-            loaded = pendRow + 1;
-            pendRow = -1;
-          }
-          // 2. rows needed now
-          PF_BEGIN;
-          int n = 0;
-          unsigned long long t0 = 0;
-          while (loaded < need && ok) {
-            if (gseen <= loaded) {
-              gseen = ld_acquire_gpu(gflagIn);
-              if (gseen <= loaded) {
-                __nanosleep(200);
-                if (((++n) & 63) == 0) {
-                  if (!t0) t0 = now_ns();
-                  if (*sAbort) { ok = false; break; }
-                  if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
+            loaded = pendEnd;
+          };
+          if (loaded < need) {  // rows needed now
+            PF_BEGIN;
+            if (pendEnd > loaded) finish();
+            int n = 0;
+            unsigned long long t0 = 0;
+            while (loaded < need && ok) {
+              const int be = blockEnd(loaded);
+              if (gseen < be) {
+                gseen = ld_acquire_gpu(gflagIn);
+                if (gseen < be) {
+                  __nanosleep(200);
+                  if (((++n) & 63) == 0) {
+                    if (!t0) t0 = now_ns();
+                    if (*sAbort) { ok = false; break; }
+                    if (now_ns() - t0 > kWaitLimitNs) { *sAbort = 1; atomicExch(a.status, 1); ok = false; break; }
+                  }
+                  continue;
                 }
-                continue;
               }
+              issue(loaded, be);
+              pendEnd = be;
+              finish();
             }
-            __syncwarp();
-            if (lane == 0) bulk_load(ring0 + (loaded & (kRingX - 1)) * ENT, gin + (size_t)loaded * ENT, ENT * 16, sBar);
-            for (int m = 0; !mbar_try_wait(sBar, barPhase);)
-              if (((++m) & 255) == 0 && *sAbort) { ok = false; break; }
+            PF_END(pfGlobal);
+          } else if (pendEnd > loaded && mbar_test_wait(sBar, barPhase)) {
             barPhase ^= 1;
-            loaded++;
+            loaded = pendEnd;
           }
-          PF_END(pfGlobal);
-          // 3. request the next row (entries T-1 and T are in use, so rows up to T+2 have a free slot)
-          if (ok && loaded <= min(T + 2, y1p)) {
-            if (gseen <= loaded) {
-              // the count is polled with a relaxed load one step ahead (no stall); only when that hint says new rows
-              // are there is it confirmed with an acquire load, which orders the copy below behind the publication
-              if (gpend > loaded) gseen = ld_acquire_gpu(gflagIn);
-              else gpend = ld_relaxed_gpu(gflagIn);
-            }
-            if (gseen > loaded) {
-              __syncwarp();
-              if (lane == 0) bulk_load(ring0 + (loaded & (kRingX - 1)) * ENT, gin + (size_t)loaded * ENT, ENT * 16, sBar);
-              pendRow = loaded;
+          // request the next block (entries T-1 and T are in use, so rows up to T + kRingX - 2 have a free slot)
+          if (ok && pendEnd <= loaded && loaded <= y1p) {
+            const int be = blockEnd(loaded);
+            if (be - 1 <= T + kRingX - 2) {
+              if (gseen < be) {
+                // the count is polled with a relaxed load one step ahead (no stall); only when that hint says the block
+                // is there is it confirmed with an acquire load, which orders the copy below behind the publication
+                if (gpend >= be) gseen = ld_acquire_gpu(gflagIn);
+                else gpend = ld_relaxed_gpu(gflagIn);
+              }
+              if (gseen >= be) { issue(loaded, be); pendEnd = be; }
             }
           }
         }
       }
-      if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - 3, sAbort, a.status); PF_END(pfRight); }
+      if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - kAhead, sAbort, a.status); PF_END(pfRight); }
       if (!ok) break;
 #if SV_SWEEP_PROF
       const long long pfq5 = clock64();
@@ -524,7 +547,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
           for (int h = 0; h < NV; h++) __stcg(gOut + v * VEC + h * LPP, eOut[v * VEC + h * LPP]);
         if (gl == 0) __stcg(gOut - gl + 4 * VEC, eMins);
       }
-      if (rightGlobal && actL && (((rL - y0L) % SV_SWEEP_PUBLISH) == SV_SWEEP_PUBLISH - 1 || rL == y1L)) {
+      if (rightGlobal && actL && ((rL % kPub) == kPub - 1 || rL == y1L)) {
         // publish: the fence makes the entries written so far visible before the counter (it also waits for this warp's
         // outstanding prefetch loads, which is why it is not done for every row)
         __threadfence();
@@ -536,6 +559,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP
     }
 #if SV_SWEEP_PROF
     pfTask += clock64() - pfStart; pfSteps += Tend - Tbeg + 1; pfT0 = clock64();
+    if (task < (int)gridDim.x && lane == 0)  // first wave: every strip group starts at the same time
+      printf("PW %d %d %d %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", (int)SECOND, blockIdx.x, warp, pfTask, pfLeft, pfRight, pfGlobal, pfIdle, pfSteps, pfA, pfB, pfBlock, pfFail, pfA1, pfA3, pfA5);
 #endif
     if (!ok && lane == 0)
       printf("svgpu sweep: cta %d warp %d task (frame %d, group %d) stopped at row step %d of [%d,%d] while waiting for %s\n", blockIdx.x, warp, frame, sg,

@@ -1,8 +1,9 @@
 import sys, collections
+tag = sys.argv[2] if len(sys.argv) > 2 else 'PF'   # PF = whole launch, PW = first task of every CTA only
 acc = collections.defaultdict(lambda: [0]*13); n = collections.Counter()
 perwarp = collections.defaultdict(lambda: [0]*13)
 for line in open(sys.argv[1]):
-    if not line.startswith('PF '): continue
+    if not line.startswith(tag + ' '): continue
     p = line.split(); sec, cta, warp = int(p[1]), int(p[2]), int(p[3]); v = list(map(int, p[4:17]))
     for i in range(13): acc[sec][i] += v[i]; perwarp[(sec, warp)][i] += v[i]
     n[sec] += 1
