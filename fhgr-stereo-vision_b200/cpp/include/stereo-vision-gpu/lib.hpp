@@ -82,6 +82,15 @@ namespace stereo_vision {
     float focal_length = 0.0f;                        ///< camera_matrix_left(0,0)
   };
 
+  /// StereoCameraInfo.hpp:15-45 without cv::Mat: what the calibration YAML holds and rectification needs (row-major).
+  struct StereoCameraInfo {
+    int width = 0, height = 0;                        ///< image_size
+    std::array<double, 9> camera_matrix_left{}, camera_matrix_right{};
+    std::array<double, 5> dist_coeffs_left{}, dist_coeffs_right{};   ///< k1 k2 p1 p2 k3
+    std::array<double, 9> R{};
+    std::array<double, 3> T{};
+  };
+
   class StereoVision {
   public:
     struct Settings {
@@ -90,7 +99,11 @@ namespace stereo_vision {
         kORB,
         kSGBM,
       };
-      Rectification rectification;                    ///< stands in for `stereo_camera_info` + the ctor's products
+      /// Either the calibration itself: the constructor then does what src/lib.cpp:32-46 does (stereoRectify on the
+      /// host, both initUndistortRectifyMap on the device) ...
+      std::optional<StereoCameraInfo> stereo_camera_info;
+      /// ... or the products of those calls, computed elsewhere (e.g. by OpenCV in the reference's constructor).
+      Rectification rectification;
       Algorithm algorithm = Algorithm::kSGBM;         ///< only kSGBM has a GPU path
       bool show_debug_info = false;
       int device = 0;                                 ///< CUDA device of this instance

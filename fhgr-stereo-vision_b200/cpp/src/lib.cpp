@@ -45,16 +45,39 @@ namespace stereo_vision {
   }  // namespace
 
   StereoVision::StereoVision(Settings settings) : settings_(std::move(settings)) {
-    auto const& r = this->settings_.rectification;
-    auto const n = static_cast<std::size_t>(r.width) * static_cast<std::size_t>(r.height);
-    if (r.width <= 0 || r.height <= 0 || r.map1_left.size() != 2 * n || r.map1_right.size() != 2 * n || r.map2_left.size() != n ||
-        r.map2_right.size() != n)
-      throw std::runtime_error("rectification maps do not match image_size");
-    svgpu_ctx* c = nullptr;
-    if (svgpu_create(this->settings_.device, r.width, r.height, &c) != SV_OK) throw std::runtime_error("no usable CUDA device for svgpu");
-    this->ctx_ = std::shared_ptr<svgpu_ctx>(c, [](svgpu_ctx* p) { svgpu_destroy(p); });
-    check(c, svgpu_set_rectify_maps(c, SV_LEFT, r.map1_left.data(), r.map2_left.data()), "svgpu_set_rectify_maps(left)");
-    check(c, svgpu_set_rectify_maps(c, SV_RIGHT, r.map1_right.data(), r.map2_right.data()), "svgpu_set_rectify_maps(right)");
+    auto& r = this->settings_.rectification;
+    auto const& info = this->settings_.stereo_camera_info;
+    if (info) {  // src/lib.cpp:29-47 from the calibration: cv::stereoRectify (host) ...
+      std::array<double, 9> R1{}, R2{};
+      std::array<double, 12> P1{}, P2{};
+      if (svgpu_stereo_rectify(info->camera_matrix_left.data(), info->dist_coeffs_left.data(), info->camera_matrix_right.data(),
+                               info->dist_coeffs_right.data(), info->width, info->height, info->R.data(), info->T.data(), R1.data(),
+                               R2.data(), P1.data(), P2.data(), r.Q.data()) != SV_OK)
+        throw std::runtime_error("stereo_camera_info cannot be rectified (degenerate calibration)");
+      r.width = info->width;
+      r.height = info->height;
+      r.baseline = static_cast<float>(std::abs(info->T[0]));          // src/lib.cpp:283
+      r.focal_length = static_cast<float>(info->camera_matrix_left[0]);  // src/lib.cpp:284
+      svgpu_ctx* c = nullptr;
+      if (svgpu_create(this->settings_.device, r.width, r.height, &c) != SV_OK) throw std::runtime_error("no usable CUDA device for svgpu");
+      this->ctx_ = std::shared_ptr<svgpu_ctx>(c, [](svgpu_ctx* p) { svgpu_destroy(p); });
+      // ... and the two cv::initUndistortRectifyMap(CV_16SC2), generated on the device
+      check(c, svgpu_init_rectify_maps(c, SV_LEFT, info->camera_matrix_left.data(), info->dist_coeffs_left.data(), R1.data(), P1.data()),
+            "svgpu_init_rectify_maps(left)");
+      check(c, svgpu_init_rectify_maps(c, SV_RIGHT, info->camera_matrix_right.data(), info->dist_coeffs_right.data(), R2.data(), P2.data()),
+            "svgpu_init_rectify_maps(right)");
+    } else {
+      auto const n = static_cast<std::size_t>(r.width) * static_cast<std::size_t>(r.height);
+      if (r.width <= 0 || r.height <= 0 || r.map1_left.size() != 2 * n || r.map1_right.size() != 2 * n || r.map2_left.size() != n ||
+          r.map2_right.size() != n)
+        throw std::runtime_error("rectification maps do not match image_size");
+      svgpu_ctx* c = nullptr;
+      if (svgpu_create(this->settings_.device, r.width, r.height, &c) != SV_OK) throw std::runtime_error("no usable CUDA device for svgpu");
+      this->ctx_ = std::shared_ptr<svgpu_ctx>(c, [](svgpu_ctx* p) { svgpu_destroy(p); });
+      check(c, svgpu_set_rectify_maps(c, SV_LEFT, r.map1_left.data(), r.map2_left.data()), "svgpu_set_rectify_maps(left)");
+      check(c, svgpu_set_rectify_maps(c, SV_RIGHT, r.map1_right.data(), r.map2_right.data()), "svgpu_set_rectify_maps(right)");
+    }
+    svgpu_ctx* c = this->ctx_.get();
     check(c, svgpu_set_Q(c, r.Q.data()), "svgpu_set_Q");
     check(c, svgpu_set_depth_consts(c, r.baseline, r.focal_length), "svgpu_set_depth_consts");
     check(c, svgpu_set_sgbm(c, &kReferenceSgbm), "svgpu_set_sgbm");

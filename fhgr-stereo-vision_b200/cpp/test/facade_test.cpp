@@ -1,6 +1,8 @@
 // facade_test — exercises the C++ facade the way the reference's gtest does (test/stereo-vision-lib-test.cpp:5-13:
 // empty images -> kInvalidImage) and, on a GPU box, one full AnalyzeAndAnnotateImage call on raw frames read from a
 // binary file written by tests/test_gpu_parity.py; prints the checksums the Python side compares with the oracle.
+// With a second file (W, H as int32, then K_l, D_l, K_r, D_r, R, T as f64) the instance is constructed from the
+// calibration instead of from precomputed maps, i.e. the constructor does all of src/lib.cpp:29-47 itself.
 #include <stereo-vision-gpu/lib.hpp>
 
 #include <cstdio>
@@ -44,6 +46,24 @@ int main(int argc, char** argv) {
   }
   std::memcpy(r.Q.data(), q.data(), sizeof(double) * 16);
   r.baseline = bf[0]; r.focal_length = bf[1];
+  if (argc > 2) {
+    std::ifstream cf(argv[2], std::ios::binary);
+    int wh[2];
+    cf.read(reinterpret_cast<char*>(wh), sizeof wh);
+    std::vector<double> v;
+    if (!read_vec(cf, v, 9 + 5 + 9 + 5 + 9 + 3)) { std::fprintf(stderr, "short calibration file\n"); return 2; }
+    StereoCameraInfo info;
+    info.width = wh[0]; info.height = wh[1];
+    double const* p = v.data();
+    std::memcpy(info.camera_matrix_left.data(), p, 9 * sizeof(double)); p += 9;
+    std::memcpy(info.dist_coeffs_left.data(), p, 5 * sizeof(double)); p += 5;
+    std::memcpy(info.camera_matrix_right.data(), p, 9 * sizeof(double)); p += 9;
+    std::memcpy(info.dist_coeffs_right.data(), p, 5 * sizeof(double)); p += 5;
+    std::memcpy(info.R.data(), p, 9 * sizeof(double)); p += 9;
+    std::memcpy(info.T.data(), p, 3 * sizeof(double));
+    s.stereo_camera_info = info;
+    s.rectification = Rectification{};  // nothing precomputed
+  }
   StereoVision const sv{s};
 
   auto const empty = sv.AnalyzeAndAnnotateImage(Image{}, Image{}, {});

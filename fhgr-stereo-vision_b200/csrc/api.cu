@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "sgbm_device.cuh"
 
@@ -293,6 +295,46 @@ SVGPU_API int svgpu_set_rectify_maps(svgpu_ctx* c, int side, const int16_t* m1, 
   CU(c, cudaMemcpyAsync(c->map1[side], m1, n * 4, cudaMemcpyHostToDevice, c->st));
   CU(c, cudaMemcpyAsync(c->map2[side], m2, n * 2, cudaMemcpyHostToDevice, c->st));
   CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_init_rectify_maps(svgpu_ctx* c, int side, const double K[9], const double D[5], const double R[9],
+                                      const double P[12]) {
+  if (!c || side < 0 || side > 1 || !K || !D || !R || !P) return fail(c, SV_INVALID_SETTINGS, "bad rectify map arguments");
+  RectifyMapArgs a;
+  if (!rectify_map_args(K, D, R, P, &a)) return fail(c, SV_INVALID_SETTINGS, "P[:3,:3] * R is singular");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)c->W * c->H;
+  if (!c->map1[side]) CU(c, cudaMalloc((void**)&c->map1[side], n * 4));
+  if (!c->map2[side]) CU(c, cudaMalloc((void**)&c->map2[side], n * 2));
+  CU(c, launch_init_rectify_map(a, c->W, c->H, c->map1[side], c->map2[side], c->st));
+  c->stats.launches++;
+  CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_get_rectify_maps(svgpu_ctx* c, int side, int16_t* m1, uint16_t* m2) {
+  if (!c || side < 0 || side > 1 || !m1 || !m2) return fail(c, SV_INVALID_SETTINGS, "bad rectify map arguments");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->map1[side] || !c->map2[side]) return fail(c, SV_NOT_CONFIGURED, "rectification maps not set");
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)c->W * c->H;
+  CU(c, cudaMemcpyAsync(m1, c->map1[side], n * 4, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(m2, c->map2[side], n * 2, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_stereo_rectify(const double K1[9], const double D1[5], const double K2[9], const double D2[5], int width,
+                                   int height, const double R[9], const double T[3], double R1[9], double R2[9], double P1[12],
+                                   double P2[12], double Q[16]) {
+  if (!K1 || !D1 || !K2 || !D2 || !R || !T || !R1 || !R2 || !P1 || !P2 || !Q || width <= 1 || height <= 1) return SV_INVALID_SETTINGS;
+  StereoRectifyOut o;
+  if (!stereo_rectify_host(K1, D1, K2, D2, width, height, R, T, &o)) return SV_INVALID_SETTINGS;
+  std::memcpy(R1, o.R1, sizeof o.R1); std::memcpy(R2, o.R2, sizeof o.R2);
+  std::memcpy(P1, o.P1, sizeof o.P1); std::memcpy(P2, o.P2, sizeof o.P2);
+  std::memcpy(Q, o.Q, sizeof o.Q);
   return SV_OK;
 }
 

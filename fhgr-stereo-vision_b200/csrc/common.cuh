@@ -63,6 +63,16 @@ size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
 
 // image_ops.cu
+struct RectifyMapArgs {
+  double iR[9];  // (P[:3,:3] * R)^-1, row-major
+  double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+};
+// rectify.cu (host)
+struct StereoRectifyOut { double R1[9], R2[9], P1[12], P2[12], Q[16]; };
+bool stereo_rectify_host(const double* K1, const double* D1, const double* K2, const double* D2, int W, int H, const double* R,
+                         const double* T, StereoRectifyOut* o);
+bool rectify_map_args(const double* K, const double* D, const double* R, const double* P, RectifyMapArgs* a);
+cudaError_t launch_init_rectify_map(const RectifyMapArgs& k, int W, int H, int16_t* map1, uint16_t* map2, cudaStream_t st);
 cudaError_t launch_remap(const uint8_t* src, int sw, int sh, size_t sstride, int cn, const int16_t* map1,
                          const uint16_t* map2, uint8_t* dst, int W, int H, size_t dstride, cudaStream_t st);
 cudaError_t launch_median3(const int16_t* src, size_t sstride, int16_t* dst, size_t dstride, int W, int H, int nframes,

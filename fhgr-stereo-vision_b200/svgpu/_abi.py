@@ -26,6 +26,7 @@ EXPORTS = (
     "svgpu_median3", "svgpu_filter_speckles", "svgpu_morph_close5", "svgpu_reproject", "svgpu_depth",
     "svgpu_prefilter_chain", "svgpu_resize", "svgpu_pipeline", "svgpu_debug_copy_volume", "svgpu_launch_count",
     "svgpu_enable_stage_timing", "svgpu_last_stage_ms", "svgpu_debug_keep_volume",
+    "svgpu_init_rectify_maps", "svgpu_get_rectify_maps", "svgpu_stereo_rectify",
 )
 
 
@@ -80,6 +81,9 @@ def load():
         "svgpu_last_error": (C.c_char_p, [vp]),
         "svgpu_version": (C.c_char_p, []),
         "svgpu_set_rectify_maps": (i, [vp, i, vp, vp]),
+        "svgpu_init_rectify_maps": (i, [vp, i, vp, vp, vp, vp]),
+        "svgpu_get_rectify_maps": (i, [vp, i, vp, vp]),
+        "svgpu_stereo_rectify": (i, [vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "svgpu_set_Q": (i, [vp, vp]),
         "svgpu_set_depth_consts": (i, [vp, C.c_float, C.c_float]),
         "svgpu_set_sgbm": (i, [vp, C.POINTER(SgbmParams)]),

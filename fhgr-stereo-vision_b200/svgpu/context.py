@@ -112,6 +112,19 @@ class Context:
             raise ValueError("map shapes must be (H,W,2) int16 and (H,W) uint16")
         self._check(self._lib.svgpu_set_rectify_maps(self._h, int(side), self._ptr(m1), self._ptr(m2)))
 
+    def init_rectify_maps(self, side, K, D, R, P):
+        """cv::initUndistortRectifyMap(K, D, R, P, size, CV_16SC2) computed on the device — src/lib.cpp:39-46."""
+        a = [np.ascontiguousarray(v, np.float64).reshape(-1) for v in (K, D, R, P)]
+        if [v.size for v in a] != [9, 5, 9, 12]:
+            raise ValueError("K 3x3, D 5 (k1 k2 p1 p2 k3), R 3x3, P 3x4 expected")
+        self._check(self._lib.svgpu_init_rectify_maps(self._h, int(side), *[self._ptr(v) for v in a]))
+
+    def get_rectify_maps(self, side):
+        m1 = np.empty((self.height, self.width, 2), np.int16)
+        m2 = np.empty((self.height, self.width), np.uint16)
+        self._check(self._lib.svgpu_get_rectify_maps(self._h, int(side), self._ptr(m1), self._ptr(m2)))
+        return m1, m2
+
     def set_Q(self, Q):
         q = np.ascontiguousarray(Q, np.float64).reshape(16)
         self._check(self._lib.svgpu_set_Q(self._h, self._ptr(q)))
@@ -302,3 +315,18 @@ class Context:
         out = np.zeros(shape, np.int16)
         self._check(self._lib.svgpu_debug_copy_volume(self._h, int(which), self._ptr(out), out.nbytes))
         return out
+
+
+def stereo_rectify(K1, D1, K2, D2, size, R, T):
+    """cv::stereoRectify(K1, D1, K2, D2, size, R, T, flags=CALIB_ZERO_DISPARITY, alpha=0) — src/lib.cpp:32-37.
+    Host arithmetic inside libsvgpu.so (needs no GPU).  size = (width, height).  Returns R1, R2, P1, P2, Q."""
+    lib = _abi.load()
+    a = [np.ascontiguousarray(v, np.float64).reshape(-1) for v in (K1, D1, K2, D2, R, T)]
+    if [v.size for v in a] != [9, 5, 9, 5, 9, 3]:
+        raise ValueError("K 3x3, D 5 (k1 k2 p1 p2 k3), R 3x3, T 3 expected")
+    out = [np.zeros(n, np.float64) for n in (9, 9, 12, 12, 16)]
+    p = lambda v: v.ctypes.data_as(C.c_void_p)
+    rc = lib.svgpu_stereo_rectify(p(a[0]), p(a[1]), p(a[2]), p(a[3]), int(size[0]), int(size[1]), p(a[4]), p(a[5]), *[p(v) for v in out])
+    if rc != _abi.SV_OK:
+        raise _abi.SvgpuError(rc, "svgpu_stereo_rectify: degenerate calibration")
+    return out[0].reshape(3, 3), out[1].reshape(3, 3), out[2].reshape(3, 4), out[3].reshape(3, 4), out[4].reshape(4, 4)

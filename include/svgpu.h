@@ -101,6 +101,19 @@ SVGPU_API const char* svgpu_version(void);
 /* the two cv::initUndistortRectifyMap(..., CV_16SC2) outputs per side, host pointers,
  * tightly packed: map1 = H*W*2 int16 (x,y), map2 = H*W uint16 (fy*32+fx). src/lib.cpp:39-46 */
 SVGPU_API int svgpu_set_rectify_maps(svgpu_ctx* ctx, int side, const int16_t* map1, const uint16_t* map2);
+/* cv::initUndistortRectifyMap(K, D, R, P, image_size, CV_16SC2, map1, map2) of one side, src/lib.cpp:39-46, computed on the
+ * device straight into the context's map storage (instead of svgpu_set_rectify_maps).  Row-major f64: K 3x3, D = k1 k2 p1
+ * p2 k3, R 3x3 (R1 / R2 of stereoRectify), P 3x4 (P1 / P2). */
+SVGPU_API int svgpu_init_rectify_maps(svgpu_ctx* ctx, int side, const double K[9], const double D[5], const double R[9],
+                                      const double P[12]);
+/* copies the maps of one side back to the host (same layout as svgpu_set_rectify_maps) */
+SVGPU_API int svgpu_get_rectify_maps(svgpu_ctx* ctx, int side, int16_t* map1, uint16_t* map2);
+/* cv::stereoRectify(K1, D1, K2, D2, image_size, R, T, R1, R2, P1, P2, Q, CALIB_ZERO_DISPARITY, alpha = 0), src/lib.cpp:32-37.
+ * Host arithmetic (one-time, a few hundred f64 operations), needs no context.  Outputs row-major: R1, R2 3x3; P1, P2 3x4;
+ * Q 4x4.  SV_INVALID_SETTINGS for a degenerate calibration (zero baseline, singular matrices). */
+SVGPU_API int svgpu_stereo_rectify(const double K1[9], const double D1[5], const double K2[9], const double D2[5], int width,
+                                   int height, const double R[9], const double T[3], double R1[9], double R2[9], double P1[12],
+                                   double P2[12], double Q[16]);
 /* Q_ from cv::stereoRectify, row-major 4x4 f64. src/lib.cpp:36 */
 SVGPU_API int svgpu_set_Q(svgpu_ctx* ctx, const double Q[16]);
 /* |T[0]| and K_left[0,0] as float. src/lib.cpp:283-284 */

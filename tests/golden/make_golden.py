@@ -210,8 +210,42 @@ def save_bottle(path):
           "post sha", hashlib.sha256(post.tobytes()).hexdigest()[:16], "valid", float((raw >= 0).mean()))
 
 
+def save_rectify(path):
+    """cv::stereoRectify(CALIB_ZERO_DISPARITY, alpha 0) + 2x cv::initUndistortRectifyMap(CV_16SC2) as the reference's
+    constructor calls them (src/lib.cpp:32-46) for seeded calibrations, plus the bottle calibration of the reference."""
+    rng = np.random.default_rng(77)
+    out = {}
+    cases = []
+    for i, (W, H) in enumerate([(200, 150), (320, 180), (161, 97), (240, 320)]):
+        f = 0.75 * W * (1 + 0.05 * rng.normal())
+        K1 = np.array([[f, 0, W / 2 + rng.normal() * 3], [0, f * (1 + 0.01 * rng.normal()), H / 2 + rng.normal() * 3], [0, 0, 1]])
+        K2 = np.array([[f * (1 + 0.01 * rng.normal()), 0, W / 2 + rng.normal() * 3], [0, f * (1 + 0.01 * rng.normal()), H / 2 + rng.normal() * 3], [0, 0, 1]])
+        D1 = np.array([rng.normal() * 0.1, rng.normal() * 0.05, 0, 0, 0]) if i % 2 == 0 else rng.normal(size=5) * np.array([0.1, 0.05, 0.002, 0.002, 0.01])
+        D2 = np.array([rng.normal() * 0.1, rng.normal() * 0.05, 0, 0, 0]) if i % 2 == 0 else rng.normal(size=5) * np.array([0.1, 0.05, 0.002, 0.002, 0.01])
+        R, _ = cv2.Rodrigues(rng.normal(size=3) * 0.02)
+        T = np.array([-120.0 + rng.normal(), rng.normal(), rng.normal()]) if i != 3 else np.array([rng.normal(), 95.0 + rng.normal(), rng.normal()])
+        cases.append((f"c{i}", K1, D1, K2, D2, R, T, W, H))
+    for tag in ("v1", "v2"):   # the reference's own calibrations
+        cal = load_calib(f"{REF}/resources/calibration/{tag}/calibration.yml")
+        W, H = cal["size"]
+        cases.append((f"ref{tag}", cal["Kl"], cal["Dl"].reshape(-1)[:5], cal["Kr"], cal["Dr"].reshape(-1)[:5], cal["R"], cal["T"].reshape(3), W, H))
+    for (n, K1, D1, K2, D2, R, T, W, H) in cases:
+        R1, R2, P1, P2, Q, _, _ = cv2.stereoRectify(K1, D1, K2, D2, (W, H), R, T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+        for k, v in dict(K1=K1, D1=D1, K2=K2, D2=D2, R=R, T=T, size=np.array([W, H]), R1=R1, R2=R2, P1=P1, P2=P2, Q=Q).items():
+            out[f"{n}_{k}"] = np.asarray(v, np.float64 if k != "size" else np.int64)
+        if not n.startswith("ref"):   # full-size maps of the reference calibration are covered by bottle.npz
+            for side, (K, D, Rr, P) in enumerate(((K1, D1, R1, P1), (K2, D2, R2, P2))):
+                m1, m2 = cv2.initUndistortRectifyMap(K, D, Rr, P, (W, H), cv2.CV_16SC2)
+                out[f"{n}_map1_{side}"] = m1
+                out[f"{n}_map2_{side}"] = m2
+    out["names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes", [c[0] for c in cases])
+
+
 if __name__ == "__main__":
-    save_sgbm(os.path.join(HERE, "sgbm_small.npz"))
-    save_bm(os.path.join(HERE, "bm_small.npz"))
-    save_stages(os.path.join(HERE, "stages_small.npz"))
-    save_bottle(os.path.join(HERE, "bottle.npz"))
+    only = sys.argv[1:]
+    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify)
+    for name, fn in jobs.items():
+        if not only or name in only:
+            fn(os.path.join(HERE, name + ".npz"))

@@ -246,8 +246,23 @@ def test_cpp_facade_matches_python_pipeline(svgpu, oracle, tmp_path):
         f.write(np.ascontiguousarray(g["scaled_right"]).tobytes())
     out = subprocess.run([exe, str(case)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    got = dict(line.split(" ", 1) for line in out.stdout.splitlines() if line.split(" ", 1)[0] in
-               ("rect_left", "rect_right", "disp", "depth", "p0", "p1"))
+    keys = ("rect_left", "rect_right", "disp", "depth", "p0", "p1")
+    got = dict(line.split(" ", 1) for line in out.stdout.splitlines() if line.split(" ", 1)[0] in keys)
+    # the same instance constructed from the calibration alone (stereoRectify on the host, maps generated on the
+    # device: all of src/lib.cpp:29-47) must produce the same bytes as the one fed with OpenCV's products
+    calib = tmp_path / "calib.bin"
+    with open(calib, "wb") as f:
+        f.write(np.array([640, 480], np.int32).tobytes())
+        for k in ("cal_Kl", "cal_Dl", "cal_Kr", "cal_Dr", "cal_R", "cal_T"):
+            a = np.ascontiguousarray(g[k], np.float64).reshape(-1)
+            f.write(a[:5].tobytes() if k in ("cal_Dl", "cal_Dr") else a.tobytes())
+    out2 = subprocess.run([exe, str(case), str(calib)], capture_output=True, text=True, timeout=120)
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    got2 = dict(line.split(" ", 1) for line in out2.stdout.splitlines() if line.split(" ", 1)[0] in keys)
+    for k in ("rect_left", "rect_right", "disp", "depth"):
+        assert got2[k] == got[k], k
+    for k in ("p0", "p1"):
+        assert np.allclose(np.array(got2[k].split(), np.float32), np.array(got[k].split(), np.float32), rtol=1e-6, atol=0), k
 
     def fnv(a):
         h = 1469598103934665603
