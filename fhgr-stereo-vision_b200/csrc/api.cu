@@ -377,11 +377,11 @@ SVGPU_API int svgpu_set_bm(svgpu_ctx* c, const svgpu_bm_params* p) {
   if (p->numDisparities <= 0 || p->numDisparities % 16 || p->numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "bm numDisparities must be a multiple of 16 in [16,256]");
   if (p->blockSize < 5 || p->blockSize % 2 == 0 || p->blockSize > 51) return fail(c, SV_INVALID_SETTINGS, "bm blockSize must be odd in [5,51]");
   if (p->preFilterCap < 1 || p->preFilterCap > 63) return fail(c, SV_INVALID_SETTINGS, "bm preFilterCap must be in [1,63]");
-  if (p->minDisparity != 0) return fail(c, SV_INVALID_SETTINGS, "bm minDisparity != 0 is not supported");
+  if (p->minDisparity < -1024 || p->minDisparity + p->numDisparities > 1024) return fail(c, SV_INVALID_SETTINGS, "bm disparity range must lie within [-1024, 1024]");
   if (p->disp12MaxDiff >= 0) return fail(c, SV_INVALID_SETTINGS, "bm disp12MaxDiff >= 0 is not supported");
   if ((long long)p->blockSize * p->blockSize * 2 * p->preFilterCap > 65535) return fail(c, SV_INVALID_SETTINGS, "bm blockSize^2*2*cap exceeds the 16-bit SAD range");
   BmCfg b{};
-  b.W = c->W; b.H = c->H; b.D = p->numDisparities; b.minD = 0; b.bs = p->blockSize; b.cap = p->preFilterCap;
+  b.W = c->W; b.H = c->H; b.D = p->numDisparities; b.minD = p->minDisparity; b.bs = p->blockSize; b.cap = p->preFilterCap;
   b.tex = p->textureThreshold; b.uniq = p->uniquenessRatio; b.d12 = p->disp12MaxDiff; b.filtered = (b.minD - 1) * 16;
   b.speckleWindowSize = p->speckleWindowSize; b.speckleRange = p->speckleRange;
   c->bm = b; c->haveBm = true;

@@ -1,6 +1,8 @@
 // bm.cu — cv::StereoBM::compute for sm_100a (BASELINE config 2; the reference never calls StereoBM,
-// grep: no "StereoBM" under /root/reference).  Arithmetic: SURVEY.md Appendix A.9, minDisparity 0,
-// XSOBEL pre-filter, no LR check.  Structure mirrors the SGBM cost kernel (sgbm.cu, K2): a CTA walks
+// grep: no "StereoBM" under /root/reference).  Arithmetic: SURVEY.md Appendix A.9, XSOBEL pre-filter, no LR check.
+// minDisparity != 0: disparity index k stands for d = k + minDisparity, i.e. the right image is read minDisparity
+// columns further left; output is produced where every window pixel has all D partners inside the image
+// (cv::getValidDisparityROI's x range) and is FILTERED elsewhere.  Structure mirrors the SGBM cost kernel (sgbm.cu, K2): a CTA walks
 // down a band of rows keeping |PL-PR| of the last blockSize+1 rows in a shared-memory ring and running
 // vertical sums; the horizontal window gives the SAD of 8 disparities per lane, and the lane group of
 // a pixel selects the winner with CREDUX without ever writing a cost volume to HBM.
@@ -56,7 +58,8 @@ __global__ void __launch_bounds__(kBmThreads) k_bm_sad(const uint8_t* __restrict
                                                        int16_t* __restrict__ disp, size_t dstride, BmCfg cfg, int rowsPerBand) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int D = cfg.D, r = cfg.bs / 2, W = cfg.W, H = cfg.H;
-  const int minX1 = D - 1, W1 = W - minX1;  // computed columns x' = x - (D-1)
+  const int minX1 = max(D - 1 + cfg.minD, 0), W1 = W - minX1;  // computed columns x' = x - minX1
+  const int xpEnd = W1 - r + min(cfg.minD, 0);                  // valid ROI in x' is [r, xpEnd)
   const BmSmem L = bm_smem_layout(D, r);
   uint32_t* sLeft = (uint32_t*)(smem + L.offLeft);
   uint16_t* sRA = (uint16_t*)(smem + L.offRA);
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kBmThreads) k_bm_sad(const uint8_t* __restrict
   const unsigned gmask = (LPP == 32) ? 0xFFFFFFFFu : (((1u << LPP) - 1u) << (lane - gl));
   const bool active = d0 < D;
   const int nslot = kBmThreads / LPP, slot = threadIdx.x / LPP;
-  const int xrMax = x0 + kBmTW - 1 + r + minX1;
+  const int xrMax = x0 + kBmTW - 1 + r + minX1 - cfg.minD;
 
   for (int i = threadIdx.x; i < NC * (D >> 3); i += kBmThreads) ((uint4*)sVs)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < NC; i += kBmThreads) sTexV[i] = 0;
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(kBmThreads) k_bm_sad(const uint8_t* __restrict
     for (int t0 = 0; t0 < kBmTW; t0 += nslot) {
       const int t = t0 + slot;
       const int xp = x0 + t, x = xp + minX1;
-      const bool on = active && slot < nslot && t < kBmTW && xp >= r && xp < W1 - r;  // valid ROI in x (A.9)
+      const bool on = active && slot < nslot && t < kBmTW && xp >= r && xp < xpEnd;  // valid ROI in x (A.9)
       uint32_t sad[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
       int tex = 0;
       if (on) {
@@ -207,8 +210,8 @@ cudaError_t bm_forward(const BmCfg& cfg, const uint8_t* left, size_t lstride, co
     k_fill_rows<<<g, 256, 0, st>>>(disp, dstride, W, H, cfg.filtered);
     (*nlaunch)++;
   }
-  const int W1 = W - (cfg.D - 1);
-  if (W1 - 2 * r <= 0 || H - 2 * r <= 0) return cudaGetLastError();
+  const int W1 = W - std::max(cfg.D - 1 + cfg.minD, 0);
+  if (W1 - 2 * r + std::min(cfg.minD, 0) <= 0 || H - 2 * r <= 0) return cudaGetLastError();
   {
     dim3 g((W + 255) / 256, H, 2);
     k_bm_prefilter<<<g, 256, 0, st>>>(left, lstride, right, rstride, pfL, pfR, W, H, cfg.cap);

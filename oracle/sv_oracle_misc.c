@@ -286,7 +286,11 @@ int svo_bm_compute(const uint8_t* left, const uint8_t* right, int W, int H, int 
     int16_t* dr = (int16_t*)((uint8_t*)disp + (size_t)y * dstride);
     for (int x = 0; x < W; x++) dr[x] = (int16_t)FILTERED;
   }
-  const int xlo = minD + D - 1 + wsz2, xhi = W - wsz2, ylo = wsz2, yhi = H - wsz2;
+  /* Computed columns: every window pixel has all D right-image partners inside the image.  This is
+   * cv::getValidDisparityROI's x range; for minDisparity != 0 OpenCV itself also emits values outside it (it indexes
+   * past the end of the image row there, so those depend on the memory layout) - here they are FILTERED. */
+  const int xlo = (minD + D - 1 > 0 ? minD + D - 1 : 0) + wsz2, xhi = W - wsz2 + (minD < 0 ? minD : 0);
+  const int ylo = wsz2, yhi = H - wsz2;
   if (xlo < xhi && ylo < yhi) {
     /* SAD volume by one integral image per disparity: sadv[(y*W+x)*D + k], k ascending == disparity descending */
     int* sadv = (int*)malloc((size_t)W * H * D * sizeof(int));

@@ -210,6 +210,27 @@ def save_bottle(path):
           "post sha", hashlib.sha256(post.tobytes()).hexdigest()[:16], "valid", float((raw >= 0).mean()))
 
 
+def save_bm_mind(path):
+    """cv2.StereoBM with minDisparity != 0.  OpenCV indexes past the end of the image rows there, so only the pixels
+    inside cv::getValidDisparityROI are reproducible; the ROI (y0, y1, x0, x1) is stored with every case."""
+    out = {}
+    n = 0
+    for (H, W, D, minD, bs, uniq) in [(60, 200, 32, 4, 9, 15), (60, 200, 32, -8, 9, 15), (80, 300, 64, 16, 15, 10), (61, 203, 32, 1, 5, 0),
+                                      (60, 200, 16, -3, 7, 15), (70, 260, 48, -40, 11, 5), (70, 260, 16, -20, 7, 15), (50, 150, 16, 33, 5, 15)]:
+        l, r = synth_pair(H, W, max(D + minD, 8), seed=H + n)
+        bm = cv2.StereoBM_create(numDisparities=D, blockSize=bs)
+        bm.setMinDisparity(minD)
+        bm.setUniquenessRatio(uniq)
+        prm = [minD, D, bs, bm.getPreFilterCap(), bm.getTextureThreshold(), uniq, 0, 0, -1]
+        w2 = bs // 2
+        out[f"l{n}"], out[f"r{n}"], out[f"p{n}"], out[f"d{n}"] = l, r, np.array(prm, np.int32), bm.compute(l, r)
+        out[f"roi{n}"] = np.array([w2, H - w2, max(minD + D - 1, 0) + w2, W - w2 + min(minD, 0)], np.int32)
+        n += 1
+    out["n"] = np.array(n)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def save_rectify(path):
     """cv::stereoRectify(CALIB_ZERO_DISPARITY, alpha 0) + 2x cv::initUndistortRectifyMap(CV_16SC2) as the reference's
     constructor calls them (src/lib.cpp:32-46) for seeded calibrations, plus the bottle calibration of the reference."""
@@ -245,7 +266,7 @@ def save_rectify(path):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify)
+    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))

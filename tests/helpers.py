@@ -37,3 +37,10 @@ def nmismatch(a, b):
 
 REF_PARAMS = dict(blockSize=7, P1=392, P2=1568, disp12MaxDiff=1, preFilterCap=32, uniquenessRatio=15,
                   speckleWindowSize=0, speckleRange=0, minDisparity=0)
+
+
+def bm_mind_golden_cases():
+    """StereoBM with minDisparity != 0: (index, left, right, params, cv2 disparity, (y0, y1, x0, x1) of cv2's valid ROI)."""
+    g = golden("bm_mind_small")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(BM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"], tuple(int(v) for v in g[f"roi{i}"])

@@ -64,6 +64,18 @@ def test_bm_golden(svgpu):
             assert nmismatch(ctx.bm(l, r), want) == 0, (i, prm)
 
 
+def test_bm_min_disparity(svgpu, oracle):
+    """StereoBM with minDisparity != 0 (positive, negative, ranges entirely below zero): equal to the oracle everywhere and to
+    cv2 inside cv::getValidDisparityROI."""
+    from helpers import bm_mind_golden_cases
+    for i, l, r, prm, want, (y0, y1, x0, x1) in bm_mind_golden_cases():
+        with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
+            ctx.set_bm(**prm)
+            got = ctx.bm(l, r)
+        assert nmismatch(got, oracle.bm(l, r, **prm)) == 0, (i, prm)
+        assert nmismatch(got[y0:y1, x0:x1], want[y0:y1, x0:x1]) == 0, (i, prm)
+
+
 def test_stages_golden(svgpu):
     g = golden("stages_small")
     with svgpu.Context(53, 37) as ctx:

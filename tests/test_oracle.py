@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import bm_golden_cases, golden, nmismatch, sgbm_golden_cases
+from helpers import bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm_golden_cases
 
 
 def test_sgbm_golden(oracle):
@@ -30,6 +30,21 @@ def test_sgbm_too_narrow_is_an_error(oracle):
 def test_bm_golden(oracle):
     for i, l, r, prm, want in bm_golden_cases():
         assert nmismatch(oracle.bm(l, r, **prm), want) == 0, (i, prm)
+
+
+def test_bm_min_disparity_golden(oracle):
+    """minDisparity != 0: bit-exact inside cv::getValidDisparityROI (outside it OpenCV's own output depends on what lies
+    behind the end of the image rows in memory; the oracle writes FILTERED there)."""
+    seen = 0
+    for i, l, r, prm, want, (y0, y1, x0, x1) in bm_mind_golden_cases():
+        got = oracle.bm(l, r, **prm)
+        assert nmismatch(got[y0:y1, x0:x1], want[y0:y1, x0:x1]) == 0, (i, prm)
+        outside = np.ones(got.shape, bool)
+        outside[y0:y1, x0:x1] = False
+        assert (got[outside] == (prm["minDisparity"] - 1) * 16).all(), (i, prm)
+        assert (got[y0:y1, x0:x1] > (prm["minDisparity"] - 1) * 16).mean() > 0.2, (i, "case has too few valid pixels")
+        seen += 1
+    assert seen >= 8
 
 
 def test_stages_golden(oracle):
