@@ -258,12 +258,20 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, 
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
   const int tiles = (cfg.W1 + TW - 1) / TW;
-  // bands: enough CTAs to fill the GPU a few times over, few enough that the 2r-row run-in stays small
-  int bands = (148 * 6 + tiles * nframes - 1) / (tiles * nframes);
-  bands = std::max(1, std::min(bands, (cfg.H + 63) / 64));
-  int rowsPerBand = (cfg.H + bands - 1) / bands;
-  rowsPerBand = (rowsPerBand + RB - 1) / RB * RB;
-  bands = (cfg.H + rowsPerBand - 1) / rowsPerBand;
+  // bands: the CTA count should fill the 148 SMs (one CTA each) in whole waves, against the 2r-row run-in that every
+  // extra band costs.  Estimated launch time in row steps = waves x (rows per band + run-in).
+  int bands = 1, rowsPerBand = cfg.H;
+  {
+    long long best = -1;
+    const int maxBands = std::max(1, std::min(16, (cfg.H + 63) / 64));
+    for (int b = 1; b <= maxBands; b++) {
+      const int rpb = ((cfg.H + b - 1) / b + RB - 1) / RB * RB;
+      const int nb = (cfg.H + rpb - 1) / rpb;
+      const long long waves = ((long long)tiles * nframes * nb + 147) / 148;
+      const long long cost = waves * (rpb + 2 * R + 4);
+      if (best < 0 || cost < best) { best = cost; bands = nb; rowsPerBand = rpb; }
+    }
+  }
   dim3 grid(tiles, bands, nframes);
   k<<<grid, (NC / COLS) * (cfg.D / kDPL), G.total, st>>>((const uint2*)sc.planesL, (const uint2*)sc.planesR, (uint4*)sc.C, cfg, rowsPerBand,
                                                          sc.frameCells / 8);
