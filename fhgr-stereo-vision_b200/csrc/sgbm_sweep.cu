@@ -31,6 +31,7 @@
 // group interleaved (word i of a group = disparities d0+i and d0+i+8), so that the d-1 / d+1 neighbours of
 // a packed register are simply the previous / next register of the lane (sgbm_device.cuh).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sgbm_device.cuh"
@@ -80,10 +81,11 @@ constexpr unsigned long long kWaitLimitNs = 10000000000ull;  // a hand-over that
 constexpr int kFlagBytes = 256;   // hand-over counters, ticket and abort flag at the end of shared memory
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kMaxNW = SV_SWEEP_MAXNW;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
+constexpr int kLowNW = 4;                   // latency variant for a few pairs per call: one warp per scheduler, twice the strip groups
 
 enum : int { P_H = 1, P_DL = 2, P_V = 4, P_DR = 8 };
 
-template <int LPP, bool SECOND>
+template <int LPP, bool SECOND, int MAXNW = kMaxNW>
 struct SweepGeom {
   static constexpr int RW = 32 / LPP;             // workers (strips) per warp
   static constexpr int NV = kNR / 4;              // uint4 per lane per path vector
@@ -99,7 +101,7 @@ struct SweepGeom {
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
   static constexpr int STAGE_U4 = 1;               // the mbarrier of the TMA copies from the left CTA's entries
   static constexpr int NW_FIT = (kSmemMax - kFlagBytes - STAGE_U4 * 16) / (WARP_U4 * 16);
-  static constexpr int NW = NW_FIT > kMaxNW ? kMaxNW : NW_FIT;  // warps per CTA
+  static constexpr int NW = NW_FIT > MAXNW ? MAXNW : NW_FIT;  // warps per CTA
   static constexpr int SPC = NW * RW;             // strips per CTA task
   static constexpr size_t SMEM = (size_t)(NW * WARP_U4 + STAGE_U4) * 16 + kFlagBytes;
 };
@@ -191,9 +193,9 @@ __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int
   return true;
 }
 
-template <int LPP, int PATHS, bool SECOND>
-__global__ void __launch_bounds__(SweepGeom<LPP, SECOND>::NW * 32, SweepGeom<LPP, SECOND>::NW <= 4 ? 2 : 1) k_sweep(const SweepArgs a) {
-  using G = SweepGeom<LPP, SECOND>;
+template <int LPP, int PATHS, bool SECOND, int MAXNW>
+__global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_sweep(const SweepArgs a) {
+  using G = SweepGeom<LPP, SECOND, MAXNW>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
   constexpr bool HAS_V = (PATHS & P_V) != 0, HAS_DL = (PATHS & P_DL) != 0, HAS_DR = (PATHS & P_DR) != 0;
   constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
@@ -582,55 +584,63 @@ int lpp_of(int D) {
 
 template <int LPP>
 struct Dims {
-  static int spc(bool second) { return second ? SweepGeom<LPP, true>::SPC : SweepGeom<LPP, false>::SPC; }
+  static int spc(bool second, bool low) {
+    if (low) return second ? SweepGeom<LPP, true, kLowNW>::SPC : SweepGeom<LPP, false, kLowNW>::SPC;
+    return second ? SweepGeom<LPP, true>::SPC : SweepGeom<LPP, false>::SPC;
+  }
   static int ent() { return SweepGeom<LPP, false>::ENT; }
 };
-int spc_of(int lpp, bool second) {
+int spc_of(int lpp, bool second, bool low) {
   switch (lpp) {
-    case 1: return Dims<1>::spc(second);
-    case 2: return Dims<2>::spc(second);
-    case 4: return Dims<4>::spc(second);
-    case 8: return Dims<8>::spc(second);
-    default: return Dims<16>::spc(second);
+    case 1: return Dims<1>::spc(second, low);
+    case 2: return Dims<2>::spc(second, low);
+    case 4: return Dims<4>::spc(second, low);
+    case 8: return Dims<8>::spc(second, low);
+    default: return Dims<16>::spc(second, low);
   }
 }
 int ent_of(int lpp) { return 4 * lpp * (kNR / 4) + 1; }
 int smax_of(const SgbmCfg& cfg) { return (cfg.W1 - 1 + cfg.H - 1) / kK; }
-int groups_of(const SgbmCfg& cfg, bool second) {
-  const int spc = spc_of(lpp_of(cfg.D), second);
+int groups_of(const SgbmCfg& cfg, bool second, bool low) {
+  const int spc = spc_of(lpp_of(cfg.D), second, low);
   return (smax_of(cfg) + 1 + spc - 1) / spc;
 }
 
-template <int LPP, int PATHS, bool SECOND>
-cudaError_t launch_one(const SweepArgs& a, int grid, cudaStream_t st) {
-  using G = SweepGeom<LPP, SECOND>;
-  auto* k = k_sweep<LPP, PATHS, SECOND>;
+template <int LPP, int PATHS, bool SECOND, int MAXNW>
+cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
+  using G = SweepGeom<LPP, SECOND, MAXNW>;
+  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return e;
   k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
+template <int LPP, int PATHS, bool SECOND>
+cudaError_t launch_one(const SweepArgs& a, bool low, int grid, cudaStream_t st) {
+  return low ? launch_nw<LPP, PATHS, SECOND, kLowNW>(a, grid, st) : launch_nw<LPP, PATHS, SECOND, kMaxNW>(a, grid, st);
+}
+
 template <int LPP>
-cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, int grid, cudaStream_t st) {
+cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, bool low, int grid, cudaStream_t st) {
   if (!second) {
-    if (paths == 15) return launch_one<LPP, 15, false>(a, grid, st);
-    return launch_one<LPP, P_H | P_V, false>(a, grid, st);
+    if (paths == 15) return launch_one<LPP, 15, false>(a, low, grid, st);
+    return launch_one<LPP, P_H | P_V, false>(a, low, grid, st);
   }
-  if (paths == 15) return launch_one<LPP, 15, true>(a, grid, st);
-  if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, true>(a, grid, st);
-  return launch_one<LPP, P_H, true>(a, grid, st);
+  if (paths == 15) return launch_one<LPP, 15, true>(a, low, grid, st);
+  if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, true>(a, low, grid, st);
+  return launch_one<LPP, P_H, true>(a, low, grid, st);
 }
 
 }  // namespace
 
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
-  return ((size_t)nframes * std::max(groups_of(cfg, false), groups_of(cfg, true)) + 64) * sizeof(int);
+  return ((size_t)nframes * std::max(groups_of(cfg, false, true), groups_of(cfg, true, true)) + 64) * sizeof(int);
 }
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
-  const int g = std::max(groups_of(cfg, false), groups_of(cfg, true));
+  const int g = std::max(groups_of(cfg, false, true), groups_of(cfg, true, true));  // the low-latency variant has the most groups
   return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
 }
 
@@ -660,19 +670,25 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   const int pass1 = cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : 15;
   const int pass2 = cfg.mode == SV_MODE_HH ? 15 : (cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : P_H);
   const int lpp = lpp_of(cfg.D);
+  // SVGPU_SWEEP_NW=4|8 pins the variant (tests run every case through both)
+  const char* ev = std::getenv("SVGPU_SWEEP_NW");
+  const int forceNW = ev ? std::atoi(ev) : 0;
   for (int pass = 0; pass < 2; pass++) {
-    a.G = groups_of(cfg, pass == 1);
+    // a few pairs per call: half as many warps per CTA give every warp its own scheduler and put twice as many SMs to work
+    bool low = (long long)nframes * groups_of(cfg, pass == 1, true) <= numSM;
+    if (forceNW) low = forceNW == kLowNW;
+    a.G = groups_of(cfg, pass == 1, low);
     cudaError_t e = cudaMemsetAsync(sc.flags, 0, ((size_t)nframes * a.G + 64) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     a.flip = pass;
     const int paths = pass ? pass2 : pass1;
     const int grid = std::min(nframes * a.G, numSM);
     switch (lpp) {
-      case 1: e = launch_lpp<1>(a, paths, pass == 1, grid, st); break;
-      case 2: e = launch_lpp<2>(a, paths, pass == 1, grid, st); break;
-      case 4: e = launch_lpp<4>(a, paths, pass == 1, grid, st); break;
-      case 8: e = launch_lpp<8>(a, paths, pass == 1, grid, st); break;
-      default: e = launch_lpp<16>(a, paths, pass == 1, grid, st); break;
+      case 1: e = launch_lpp<1>(a, paths, pass == 1, low, grid, st); break;
+      case 2: e = launch_lpp<2>(a, paths, pass == 1, low, grid, st); break;
+      case 4: e = launch_lpp<4>(a, paths, pass == 1, low, grid, st); break;
+      case 8: e = launch_lpp<8>(a, paths, pass == 1, low, grid, st); break;
+      default: e = launch_lpp<16>(a, paths, pass == 1, low, grid, st); break;
     }
     if (stats) stats->launches++;
     if (e != cudaSuccess) return e;

@@ -301,11 +301,14 @@ def test_cpp_facade_matches_python_pipeline(svgpu, oracle, tmp_path):
         assert np.allclose(np.array(got[key].split(), np.float32), want, rtol=1e-6, atol=0), (key, got[key], want)
 
 
-def test_sgbm_random_configs_bit_exact(svgpu, oracle):
+@pytest.mark.parametrize("sweep_nw", ["8", "4"])
+def test_sgbm_random_configs_bit_exact(svgpu, oracle, sweep_nw, monkeypatch):
     """Seeded random sweep over image sizes (incl. fewer computed columns than one strip and single-row images),
     disparity ranges, block sizes, penalties, uniqueness ratios, minDisparity signs and all three modes, on textured
-    and on saturating noise inputs: bit-exact against the oracle."""
+    and on saturating noise inputs: bit-exact against the oracle.  Run once per build of the sweep kernel: 8 warps per
+    CTA (throughput) and 4 (the low-latency variant the library picks by itself for a few pairs per call)."""
     from svgpu.synth import synth_pair
+    monkeypatch.setenv("SVGPU_SWEEP_NW", sweep_nw)
     rng = np.random.default_rng(20261018)
     bad = []
     for case in range(48):

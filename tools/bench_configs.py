@@ -36,6 +36,13 @@ def sgbm(W, H, D, mode, B):
 
 
 if __name__ == "__main__":
+    if "--latency" in sys.argv:   # one pair per call, the way the reference's front-ends call the library
+        for (W, H, D, mode, name) in [(640, 480, 224, 3, "reference 640x480 D=224 HH4"), (1280, 720, 64, 0, "config 2 1280x720 D=64 SGBM"),
+                                      (1920, 1080, 128, 1, "config 3 1920x1080 D=128 HH"), (3840, 2160, 256, 1, "config 4 3840x2160 D=256 HH")]:
+            for B in (1, 2, 4):
+                fps, _ = sgbm(W, H, D, mode, B)
+                print(f"{name}: {B} pair(s) per call: {B / fps * 1e3:7.2f} ms per call, {fps:7.1f} fps", flush=True)
+        sys.exit(0)
     fps, mpd = sgbm(1280, 720, 64, 0, 64); print(f"config 2  SGBM MODE_SGBM 1280x720 D=64, 64 pairs/step: {fps:8.1f} fps {mpd:10.0f} Mpix*disp/s")
     fps, mpd = sgbm(1280, 720, 64, 1, 64); print(f"          SGBM MODE_HH   1280x720 D=64, 64 pairs/step: {fps:8.1f} fps {mpd:10.0f} Mpix*disp/s")
     fps, mpd = sgbm(640, 480, 224, 3, 64); print(f"reference SGBM MODE_HH4  640x480 D=224, 64 pairs/step: {fps:8.1f} fps {mpd:10.0f} Mpix*disp/s")
