@@ -36,6 +36,7 @@ struct svgpu_ctx {
   int allocBatch = 0;
   size_t allocCells = 0;
   int allocWp = 0;
+  int allocCn = 0;   // colour channels the operand planes are sized for
   // device staging of caller images for SV_MEM_HOST calls and intermediates of the fused chain
   std::vector<void*> pool;  // everything cudaMalloc'ed lazily through dev_buf()
   struct Buf { void* p = nullptr; size_t n = 0; };
@@ -81,7 +82,7 @@ void free_scratch(svgpu_ctx* c) {
   cudaFree(c->sc.planesL); cudaFree(c->sc.planesR); cudaFree(c->sc.C); cudaFree(c->sc.S); cudaFree(c->sc.sel);
   cudaFree(c->sc.dispRaw); cudaFree(c->sc.status); cudaFree(c->sc.flags); cudaFree(c->sc.edges);
   c->sc = SgbmScratch{};
-  c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0;
+  c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0; c->allocCn = 0;
 }
 
 // the sweep kernels raise sc.status when a hand-over timed out (which would mean a scheduling bug or a device
@@ -99,12 +100,14 @@ int check_status(svgpu_ctx* c) {
   return SV_OK;
 }
 
-int ensure_scratch(svgpu_ctx* c, int batch) {
+int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   const SgbmCfg& g = c->cfg;
   const size_t cells = g.W1 > 0 ? (size_t)g.W1 * g.H * g.D : 0;
-  if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->sc.dispRaw) return SV_OK;
+  if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->allocCn >= cn && c->sc.dispRaw) return SV_OK;
+  batch = std::max(batch, c->allocBatch);
+  cn = std::max(cn, c->allocCn);
   free_scratch(c);
-  const size_t planeBytes = (size_t)batch * g.H * 2 * g.Wp * sizeof(uint2);
+  const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2);
   const size_t w1 = g.W1 > 0 ? g.W1 : 0;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 256)); };
@@ -122,7 +125,7 @@ int ensure_scratch(svgpu_ctx* c, int batch) {
   cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(g, batch), c->st);
   cudaMemsetAsync(c->sc.edges, 0, sgbm_edges_bytes(g, batch), c->st);  // launch tags start at 1
   c->sc.frameCells = cells;
-  c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp;
+  c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp; c->allocCn = cn;
   return SV_OK;
 }
 
@@ -172,16 +175,19 @@ int d2h_2d(svgpu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitc
 }
 
 int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const uint8_t* dr, size_t rs, size_t rf,
-             int16_t* dd, size_t ds, size_t df) {
+             int16_t* dd, size_t ds, size_t df, int cn = 1) {
+  // 8UC3 input: the pixel cost is the sum over the three channels, so the 16-bit headroom shrinks accordingly
+  if (cn == 3 && (long long)(2 * c->cfg.r + 1) * (2 * c->cfg.r + 1) * 3 * (2 * c->cfg.ftzero + 63) + c->cfg.P2 > 32767)
+    return fail(c, SV_INVALID_SETTINGS, "3 * blockSize^2*(2*ftzero+63) + P2 exceeds the 16-bit cost range for 3-channel input");
   // cv::StereoSGBM::compute throws for MODE_SGBM / MODE_HH when the image is too narrow for the
   // disparity range ('width - (minDisparity + numDisparities) > SADWindowSize/2'); MODE_HH4 returns an
   // all-invalid map instead.  Same behaviour here, as an error code.
   if (c->cfg.mode != SV_MODE_HH4 && c->W - (c->cfg.minD + c->cfg.D) <= c->cfg.r)
     return fail(c, SV_INVALID_SETTINGS, "image too narrow for minDisparity + numDisparities and blockSize");
-  int rc = ensure_scratch(c, std::max(n, c->maxBatch));
+  int rc = ensure_scratch(c, std::max(n, c->maxBatch), cn);
   if (rc) return rc;
   cudaError_t e = sgbm_forward(c->cfg, c->sc, n, dl, ls, lf, dr, rs, rf, dd, ds, df, c->st, &c->stats,
-                               c->timing ? c->ev : nullptr, c->debugS ? 1 : 0);
+                               c->timing ? c->ev : nullptr, c->debugS ? 1 : 0, cn);
   if (e != cudaSuccess) return cuda_fail(c, e, "sgbm_forward");
   if (c->cfg.speckleWindowSize > 0) {  // built-in stage of StereoSGBM::compute (A.7): newVal = INVALID, maxDiff = 16*range
     rc = ensure(c, c->stLabels, (size_t)c->W * c->H * 4);
@@ -716,7 +722,6 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
   const int cn = io->channels;
   if (cn != 1 && cn != 3) return fail(c, SV_INVALID_SETTINGS, "channels must be 1 or 3");
   if ((stages & SV_STAGE_PREFILTER) && cn != 3) return fail(c, SV_INVALID_SETTINGS, "the pre-filter chain needs BGR input");
-  if (!(stages & SV_STAGE_PREFILTER) && (stages & SV_STAGE_SGBM) && cn != 1) return fail(c, SV_INVALID_SETTINGS, "SGBM without the pre-filter chain needs 8UC1 input");
   if ((stages & SV_STAGE_SGBM) && !c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
   if ((stages & SV_STAGE_REMAP) && (!c->map1[0] || !c->map1[1])) return fail(c, SV_NOT_CONFIGURED, "rectify maps not set");
   if ((stages & SV_STAGE_REPROJECT) && !c->haveQ) return fail(c, SV_NOT_CONFIGURED, "Q not set");
@@ -767,7 +772,8 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
     dd = (int16_t*)c->stDisp.p; dds = W * 2;
   }
   if (stages & SV_STAGE_SGBM) {
-    rc = run_sgbm(c, 1, curL, curLs, 0, curR, curRs, 0, dd, dds, 0); if (rc) return rc;
+    // without the pre-filter chain a BGR pair goes to StereoSGBM as it is (cv::StereoSGBM::compute on 8UC3 images)
+    rc = run_sgbm(c, 1, curL, curLs, 0, curR, curRs, 0, dd, dds, 0, (stages & SV_STAGE_PREFILTER) ? 1 : cn); if (rc) return rc;
   }
   if (stages & SV_STAGE_POSTFILTER) {
     // src/lib.cpp:264 is a no-op for SGBM output (invalid = -16, never -1); :265 and :267-268 follow

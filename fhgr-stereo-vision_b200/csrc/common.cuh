@@ -53,9 +53,9 @@ struct LaunchStats {
 // sgbm.cu
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
-                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS);
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS, int cn = 1);
 // sgbm_cost.cu: Birchfield-Tomasi pixel cost + box sum -> cost volume
-cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st);
+cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int cn, cudaStream_t st);
 // sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats);

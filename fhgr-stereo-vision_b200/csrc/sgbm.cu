@@ -24,46 +24,52 @@ namespace svgpu {
 // ------------------------------------------------------------------------------------------------
 // K1: pre-filter (A.2) + Birchfield-Tomasi half-pixel bounds (A.3) -> operand planes
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int pf_grad(const uint8_t* r, const uint8_t* u, const uint8_t* d, int x, int W, int ftzero) {
+// r / u / d point at the wanted channel of pixel 0 of the row / the row above / below; `cn` interleaved channels
+__device__ __forceinline__ int pf_grad(const uint8_t* r, const uint8_t* u, const uint8_t* d, int x, int W, int cn, int ftzero) {
   if (x <= 0 || x >= W - 1) return ftzero;
-  int v = 2 * ((int)r[x + 1] - (int)r[x - 1]) + ((int)u[x + 1] - (int)u[x - 1]) + ((int)d[x + 1] - (int)d[x - 1]);
+  const int a = (x + 1) * cn, b = (x - 1) * cn;
+  int v = 2 * ((int)r[a] - (int)r[b]) + ((int)u[a] - (int)u[b]) + ((int)d[a] - (int)d[b]);
   return min(max(v, -ftzero), ftzero) + ftzero;
 }
-__device__ __forceinline__ int pf_int(const uint8_t* r, int x, int W, int ftzero) {
-  return (x <= 0 || x >= W - 1) ? ftzero : (int)r[x];
+__device__ __forceinline__ int pf_int(const uint8_t* r, int x, int W, int cn, int ftzero) {
+  return (x <= 0 || x >= W - 1) ? ftzero : (int)r[x * cn];
 }
 
+// Plane order of a row: [channel][gradient, intensity][Wp] (cn = 3: StereoSGBM sums the cost over the colour channels,
+// each with its own gradient and intensity term)
 __global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restrict__ left, size_t lstride, size_t lframe,
                                                           const uint8_t* __restrict__ right, size_t rstride, size_t rframe,
                                                           uint8_t* __restrict__ planesL, uint8_t* __restrict__ planesR,
-                                                          int W, int H, int Wp, int ftzero) {
+                                                          int W, int H, int Wp, int cn, int ftzero) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
   if (x >= W) return;
   const uint8_t* img = side ? right + frame * rframe : left + frame * lframe;
   const size_t stride = side ? rstride : lstride;
-  const uint8_t* r = img + (size_t)y * stride;
-  const uint8_t* u = y > 0 ? r - stride : r;
-  const uint8_t* d = y < H - 1 ? r + stride : r;
-  const int g0 = pf_grad(r, u, d, x, W, ftzero), i0 = pf_int(r, x, W, ftzero);
-  int glo = g0, ghi = g0, ilo = i0, ihi = i0;
-  if (x > 0) {
-    const int g = (g0 + pf_grad(r, u, d, x - 1, W, ftzero)) >> 1, i = (i0 + pf_int(r, x - 1, W, ftzero)) >> 1;
-    glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
-  }
-  if (x < W - 1) {
-    const int g = (g0 + pf_grad(r, u, d, x + 1, W, ftzero)) >> 1, i = (i0 + pf_int(r, x + 1, W, ftzero)) >> 1;
-    glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
-  }
   auto h16 = [](int v) { return (uint32_t)v & 0xFFFFu; };
-  uint2* p = (uint2*)(side ? planesR : planesL) + ((size_t)frame * H + y) * 2 * Wp + x;
-  if (side == 0) {
-    p[0] = make_uint2(h16(glo) | h16(g0) << 16, h16(-ghi) | h16(-g0) << 16);
-    p[Wp] = make_uint2(h16(ilo) | h16(i0) << 16, h16(-ihi) | h16(-i0) << 16);
-  } else {
-    p[0] = make_uint2(h16(-g0) | h16(-ghi) << 16, h16(g0) | h16(glo) << 16);
-    p[Wp] = make_uint2(h16(-i0) | h16(-ihi) << 16, h16(i0) | h16(ilo) << 16);
+  uint2* p = (uint2*)(side ? planesR : planesL) + ((size_t)frame * H + y) * 2 * cn * Wp + x;
+  for (int c = 0; c < cn; c++, p += 2 * Wp) {
+    const uint8_t* r = img + (size_t)y * stride + c;
+    const uint8_t* u = y > 0 ? r - stride : r;
+    const uint8_t* d = y < H - 1 ? r + stride : r;
+    const int g0 = pf_grad(r, u, d, x, W, cn, ftzero), i0 = pf_int(r, x, W, cn, ftzero);
+    int glo = g0, ghi = g0, ilo = i0, ihi = i0;
+    if (x > 0) {
+      const int g = (g0 + pf_grad(r, u, d, x - 1, W, cn, ftzero)) >> 1, i = (i0 + pf_int(r, x - 1, W, cn, ftzero)) >> 1;
+      glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
+    }
+    if (x < W - 1) {
+      const int g = (g0 + pf_grad(r, u, d, x + 1, W, cn, ftzero)) >> 1, i = (i0 + pf_int(r, x + 1, W, cn, ftzero)) >> 1;
+      glo = min(glo, g); ghi = max(ghi, g); ilo = min(ilo, i); ihi = max(ihi, i);
+    }
+    if (side == 0) {
+      p[0] = make_uint2(h16(glo) | h16(g0) << 16, h16(-ghi) | h16(-g0) << 16);
+      p[Wp] = make_uint2(h16(ilo) | h16(i0) << 16, h16(-ihi) | h16(-i0) << 16);
+    } else {
+      p[0] = make_uint2(h16(-g0) | h16(-ghi) << 16, h16(g0) | h16(glo) << 16);
+      p[Wp] = make_uint2(h16(-i0) | h16(-ihi) << 16, h16(i0) | h16(ilo) << 16);
+    }
   }
 }
 
@@ -134,7 +140,7 @@ __global__ void k_fill_rows_s16(int16_t* p, size_t stride, size_t frame, int W, 
 
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
-                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS) {
+                         size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS, int cn) {
   const int W = cfg.W, H = cfg.H;
   if (cfg.W1 <= 0) {  // A.1: nothing computable, whole map invalid
     dim3 g((W + 255) / 256, H, nframes);
@@ -146,10 +152,10 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
   {
     dim3 g((W + 255) / 256, H, nframes * 2);
     k_prefilter_planes<<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H,
-                                          cfg.Wp, cfg.ftzero);
+                                          cfg.Wp, cn, cfg.ftzero);
     SV_LAUNCHED();
   }
-  SV_RET(sgbm_cost_volume(cfg, sc, nframes, st));
+  SV_RET(sgbm_cost_volume(cfg, sc, nframes, cn, st));
   if (stats) stats->launches++;
   if (ev) SV_RET(cudaEventRecord(ev[1], st));
   SV_RET(sgbm_aggregate_sweep(cfg, sc, nframes, debugS, st, stats));

@@ -38,15 +38,16 @@ struct CostGeom {
   int rowU4;   // uint4 per (row, half-group) line of the Vs buffer: NC + 1 (padding against bank conflicts)
   size_t offL, offR, offV, total;  // byte offsets in dynamic shared memory
 };
-template <int NC, int RB>
+// CH = operand planes per image row: 2 (gradient, intensity) per colour channel
+template <int NC, int RB, int CH>
 __host__ __device__ inline CostGeom cost_geom(int D) {
   CostGeom g;
   g.ng = D / kDPL;
   g.NJ = NC + D - 9;
   g.rowU4 = NC + 1;
-  g.offL = 0;                                        // [2 rows][2 channels][NC] uint4
-  g.offR = g.offL + (size_t)2 * 2 * NC * 16;         // [2 rows][2 channels][NJ] uint4
-  g.offV = g.offR + (size_t)2 * 2 * g.NJ * 16;       // [RB][ng*2][NC+1] uint4
+  g.offL = 0;                                        // [2 rows][CH planes][NC] uint4
+  g.offR = g.offL + (size_t)2 * CH * NC * 16;        // [2 rows][CH planes][NJ] uint4
+  g.offV = g.offR + (size_t)2 * CH * g.NJ * 16;      // [RB][ng*2][NC+1] uint4
   g.total = g.offV + (size_t)RB * g.ng * 2 * g.rowU4 * 16;
   return g;
 }
@@ -60,13 +61,13 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
 
 // COLS neighbouring columns per thread: 8 of the 9 right-image records of two neighbouring columns are the same,
 // so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
-template <int R, int NC, int COLS, int RB, int ITEMS>
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
 __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
                                                                 uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
   extern __shared__ uint4 smemU4[];
   const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
-  const CostGeom G = cost_geom<NC, RB>(D);
+  const CostGeom G = cost_geom<NC, RB, CH>(D);
   uint4* sL = smemU4 + G.offL / 16;
   uint4* sR = smemU4 + G.offR / 16;
   uint4* sV = smemU4 + G.offV / 16;
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * TW;                  // first output column x' of the tile
   const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
-  const uint2* pL = planesL + (size_t)frame * H * 2 * Wp;
-  const uint2* pR = planesR + (size_t)frame * H * 2 * Wp;
+  const uint2* pL = planesL + (size_t)frame * H * CH * Wp;
+  const uint2* pR = planesR + (size_t)frame * H * CH * Wp;
   uint4* Cf = Cvol + (size_t)frame * frameU4;
 
   // ---- pixel-cost mapping: lanes = neighbouring column groups, thread = (COLS columns, 16 disparities)
@@ -105,14 +106,14 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
     const int it = tid + q * nthr;
     itOffA[q] = itOffB[q] = 0;
     itDst[q] = -1;
-    if (it < 2 * NC) {
+    if (it < CH * NC) {
       const int ch = it / NC, cc = it % NC;
       // columns outside the volume are computed on some valid pixel and ignored by the horizontal phase
       itOffA[q] = ch * Wp + min(max(x0 - R + cc + cfg.minX1, 0), cfg.W - 1);
       itDst[q] = ch * NC + cc;
       itLeft |= 1u << q;
-    } else if (it < 2 * NC + 2 * NJ) {
-      const int k = it - 2 * NC, ch = k / NJ, j = k % NJ;
+    } else if (it < CH * NC + CH * NJ) {
+      const int k = it - CH * NC, ch = k / NJ, j = k % NJ;
       // positions outside the image only ever pair with cells outside the volume: any in-range word will do
       itOffA[q] = ch * Wp + min(max(xrMax - j, 0), cfg.W - 1);
       itOffB[q] = ch * Wp + min(max(xrMax - j - 8, 0), cfg.W - 1);
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
   }
   uint2 stA[ITEMS], stB[ITEMS];
   auto stage_load = [&](int yy) {
-    const uint2* rowL = pL + (size_t)yy * 2 * Wp;
-    const uint2* rowR = pR + (size_t)yy * 2 * Wp;
+    const uint2* rowL = pL + (size_t)yy * CH * Wp;
+    const uint2* rowR = pR + (size_t)yy * CH * Wp;
 #pragma unroll
     for (int q = 0; q < ITEMS; q++) {
       if (itDst[q] < 0) continue;
@@ -139,15 +140,18 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
     for (int q = 0; q < ITEMS; q++) {
       if (itDst[q] < 0) continue;
       if ((itLeft >> q) & 1)
-        sL[b * 2 * NC + itDst[q]] = make_uint4(__byte_perm(stA[q].x, 0, 0x1010), __byte_perm(stA[q].x, 0, 0x3232),
+        sL[b * CH * NC + itDst[q]] = make_uint4(__byte_perm(stA[q].x, 0, 0x1010), __byte_perm(stA[q].x, 0, 0x3232),
                                                __byte_perm(stA[q].y, 0, 0x1010), __byte_perm(stA[q].y, 0, 0x3232));
       else
-        sR[b * 2 * NJ + itDst[q]] = make_uint4(__byte_perm(stA[q].x, stB[q].x, 0x5410), __byte_perm(stA[q].x, stB[q].x, 0x7632),
+        sR[b * CH * NJ + itDst[q]] = make_uint4(__byte_perm(stA[q].x, stB[q].x, 0x5410), __byte_perm(stA[q].x, stB[q].x, 0x7632),
                                                __byte_perm(stA[q].y, stB[q].y, 0x5410), __byte_perm(stA[q].y, stB[q].y, 0x7632));
     }
   };
 
-  uint32_t Vs[COLS][kNR], pix[COLS][kNR], ring[NRING][COLS][kNR / 2];
+  // the pixel costs of the last 2r+1 rows: one byte per cost for a single channel (<= 2*63 + 63), 16 bits for three
+  constexpr bool RING8 = CH == 2;
+  constexpr int RINGW = RING8 ? kNR / 2 : kNR;
+  uint32_t Vs[COLS][kNR], pix[COLS][kNR], ring[NRING][COLS][RINGW];
 #pragma unroll
   for (int m = 0; m < COLS; m++) {
 #pragma unroll
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
 #pragma unroll
     for (int k = 0; k < NRING; k++)
 #pragma unroll
-      for (int i = 0; i < kNR / 2; i++) ring[k][m][i] = 0;
+      for (int i = 0; i < RINGW; i++) ring[k][m][i] = 0;
   }
 
   const int vbeg = yb - R, vend = ye - 1 + R;  // virtual rows whose pixel costs enter the band's sums
@@ -179,9 +183,9 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
       //      records j0 + (COLS-1-m) + i, i = 0..7: record q of this thread serves register q - (COLS-1-m) of column m
       if (yy != computed) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-          const uint4* lrec = sL + ((yy & 1) * 2 + ch) * NC + c0;
-          const uint4* rrec = sR + ((yy & 1) * 2 + ch) * NJ + j0;
+        for (int ch = 0; ch < CH; ch++) {
+          const uint4* lrec = sL + ((yy & 1) * CH + ch) * NC + c0;
+          const uint4* rrec = sR + ((yy & 1) * CH + ch) * NJ + j0;
           uint4 lu[COLS];
 #pragma unroll
           for (int m = 0; m < COLS; m++) lu[m] = lrec[m];
@@ -194,7 +198,8 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
               if (i >= 0 && i < kNR) {
                 const uint32_t cst = bt_cost(lu[m], rr);
                 if (ch == 0) pix[m][i] = cst;
-                else pix[m][i] += (cst >> 2) & 0x3FFF3FFFu;
+                else if (ch & 1) pix[m][i] += (cst >> 2) & 0x3FFF3FFFu;  // intensity term: a quarter of the weight
+                else pix[m][i] += cst;
               }
             }
           }
@@ -206,12 +211,20 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
       const int y = v - R;  // output row completed by this virtual row
 #pragma unroll
       for (int m = 0; m < COLS; m++) {
+        if constexpr (RING8) {
 #pragma unroll
-        for (int i = 0; i < kNR / 2; i++) {
-          const uint32_t old = ring[k][m][i];
-          Vs[m][2 * i] += pix[m][2 * i] - __byte_perm(old, 0, 0x4140);
-          Vs[m][2 * i + 1] += pix[m][2 * i + 1] - __byte_perm(old, 0, 0x4342);
-          ring[k][m][i] = __byte_perm(pix[m][2 * i], pix[m][2 * i + 1], 0x6420);
+          for (int i = 0; i < kNR / 2; i++) {
+            const uint32_t old = ring[k][m][i];
+            Vs[m][2 * i] += pix[m][2 * i] - __byte_perm(old, 0, 0x4140);
+            Vs[m][2 * i + 1] += pix[m][2 * i + 1] - __byte_perm(old, 0, 0x4342);
+            ring[k][m][i] = __byte_perm(pix[m][2 * i], pix[m][2 * i + 1], 0x6420);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kNR; i++) {
+            Vs[m][i] += pix[m][i] - ring[k][m][i];
+            ring[k][m][i] = pix[m][i];
+          }
         }
         if (y >= yb) {
           uint4* dst = sV + ((size_t)((y - yb) % RB) * ng * 2 + g * 2) * G.rowU4 + vpos(c0 + m);
@@ -250,10 +263,10 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
   }
 }
 
-template <int R, int NC, int COLS, int RB, int ITEMS>
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
 cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
-  const CostGeom G = cost_geom<NC, RB>(cfg.D);
-  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS>;
+  const CostGeom G = cost_geom<NC, RB, CH>(cfg.D);
+  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
@@ -278,23 +291,29 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, 
   return cudaGetLastError();
 }
 
-template <int NC, int COLS, int RB, int ITEMS>
+template <int NC, int COLS, int RB, int ITEMS, int CH = 2>
 cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
-    case 3: return launch_cost<3, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
-    case 4: return launch_cost<4, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
-    default: return launch_cost<5, NC, COLS, RB, ITEMS>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    case 3: return launch_cost<3, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    case 4: return launch_cost<4, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    default: return launch_cost<5, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
   }
 }
 
 }  // namespace
 
 // Ctrue of `nframes` pairs from their pre-filter planes
-cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
-  // records staged per thread and row = (2 NC + 2 NJ) / threads
+cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int cn, cudaStream_t st) {
+  // records staged per thread and row = (CH NC + CH NJ) / threads, CH = 2 planes per colour channel
+  if (cn == 3) {
+    if (cfg.D > 128) return launch_cost_r<32, 1, 8, 6, 6>(cfg, sc, nframes, st);
+    if (cfg.D == 128) return launch_cost_r<64, 1, 8, 3, 6>(cfg, sc, nframes, st);
+    if (cfg.D >= 48) return launch_cost_r<64, 1, 8, 6, 6>(cfg, sc, nframes, st);
+    return launch_cost_r<64, 1, 8, 15, 6>(cfg, sc, nframes, st);
+  }
 #if SV_COST_COLS == 2
   // two columns per thread, 32 column pairs x D/16 groups <= 256 threads, two CTAs per SM
   if (cfg.D > 128) return launch_cost_r<32, 2, 4, 3>(cfg, sc, nframes, st);   // 16 pairs x <= 16 groups

@@ -174,7 +174,10 @@ class Context:
         return left, right
 
     def sgbm(self, left, right):
-        """cv::StereoSGBM::compute — src/lib.cpp:262."""
+        """cv::StereoSGBM::compute — src/lib.cpp:262.  8UC1 pairs (what the reference passes) or 8UC3 pairs (OpenCV then sums
+        the matching cost over the three channels; goes through svgpu_pipeline with SV_STAGE_SGBM alone)."""
+        if len(left.shape) == 3 and int(left.shape[2]) == 3:
+            return self.pipeline(left, right, _abi.STAGE_SGBM)["disp"]
         left, right = self._pair(left, right)
         disp = self._out_like(left, (self.height, self.width), np.int16)
         self._check(self._lib.svgpu_sgbm_compute(self._h, self._ptr(left), self._stride(left), self._ptr(right),

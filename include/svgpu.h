@@ -163,7 +163,8 @@ SVGPU_API int svgpu_resize(svgpu_ctx* ctx, const uint8_t* src, int src_width, in
 enum {
   SV_STAGE_REMAP = 1,      /* src/lib.cpp:87-94: inputs are raw 8UC3 frames, rectified on the fly   */
   SV_STAGE_PREFILTER = 2,  /* src/lib.cpp:231-246: blur + gray + sharpen (else inputs must be 8UC1) */
-  SV_STAGE_SGBM = 4,       /* src/lib.cpp:248-262                                                  */
+  SV_STAGE_SGBM = 4,       /* src/lib.cpp:248-262; without SV_STAGE_PREFILTER an 8UC3 pair goes to
+                            * StereoSGBM as it is (cost summed over the three channels)             */
   SV_STAGE_POSTFILTER = 8, /* src/lib.cpp:264-268: filterSpeckles(0,150,32) + close 5x5            */
   SV_STAGE_REPROJECT = 16, /* src/lib.cpp:152-156                                                  */
   SV_STAGE_DEPTH = 32      /* src/lib.cpp:279-294                                                  */

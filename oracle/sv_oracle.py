@@ -57,10 +57,11 @@ def _u8(a):
 def sgbm(left, right, **kw):
     """cv::StereoSGBM::compute — src/lib.cpp:248-262."""
     left, right = _u8(left), _u8(right)
-    H, W = left.shape
+    H, W = left.shape[:2]
+    cn = 1 if left.ndim == 2 else left.shape[2]   # 8UC1 (the reference's call) or 8UC3
     prm = SgbmParams(**kw)
     disp = np.empty((H, W), np.int16)
-    rc = lib().svo_sgbm_compute(_p(left), _p(right), W, H, W, W, C.byref(prm), _p(disp), W * 2)
+    rc = lib().svo_sgbm_compute_cn(_p(left), _p(right), W, H, W * cn, W * cn, cn, C.byref(prm), _p(disp), W * 2)
     if rc:
         raise ValueError(f"svo_sgbm_compute rc={rc}")
     return disp

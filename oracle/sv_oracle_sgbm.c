@@ -16,7 +16,9 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 /* A.2: pre-filter rows. g = clipped x-Sobel, i = intensity; both = ftzero at x=0 and x=W-1 */
-static void prefilter(const uint8_t* img, int W, int H, int stride, int ftzero, uint8_t* g, uint8_t* it) {
+/* `img` points at channel c of an image with `cn` interleaved channels (calcPixelCostBT treats every channel of an
+ * 8UC3 input as a plane of its own: row1[x*3 + c]) */
+static void prefilter(const uint8_t* img, int W, int H, int stride, int cn, int ftzero, uint8_t* g, uint8_t* it) {
   for (int y = 0; y < H; y++) {
     const uint8_t* r = img + (size_t)y * stride;
     const uint8_t* u = y > 0 ? r - stride : r;
@@ -24,9 +26,10 @@ static void prefilter(const uint8_t* img, int W, int H, int stride, int ftzero, 
     uint8_t* gy = g + (size_t)y * W;
     uint8_t* iy = it + (size_t)y * W;
     for (int x = 1; x < W - 1; x++) {
-      int v = 2 * (r[x + 1] - r[x - 1]) + (u[x + 1] - u[x - 1]) + (d[x + 1] - d[x - 1]);
+      const int a = (x + 1) * cn, b = (x - 1) * cn;
+      int v = 2 * (r[a] - r[b]) + (u[a] - u[b]) + (d[a] - d[b]);
       gy[x] = (uint8_t)(iclamp(v, -ftzero, ftzero) + ftzero);
-      iy[x] = r[x];
+      iy[x] = r[x * cn];
     }
     gy[0] = iy[0] = (uint8_t)ftzero;
     if (W > 1) gy[W - 1] = iy[W - 1] = (uint8_t)ftzero;
@@ -56,6 +59,13 @@ int16_t* svo_debug_S = 0;
 
 int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, int lstride, int rstride,
                      const svo_sgbm_params* prm, int16_t* disp, int dstride) {
+  return svo_sgbm_compute_cn(left, right, W, H, lstride, rstride, 1, prm, disp, dstride);
+}
+
+/* cn = 1 (8UC1, what the reference passes, src/lib.cpp:262) or 3 (8UC3: StereoSGBM sums the pixel cost of the three
+ * channels, each with its own gradient and intensity term) */
+int svo_sgbm_compute_cn(const uint8_t* left, const uint8_t* right, int W, int H, int lstride, int rstride, int cn,
+                        const svo_sgbm_params* prm, int16_t* disp, int dstride) {
   /* A.1 parameter normalisation */
   const int minD = prm->minDisparity, D = prm->numDisparities, maxD = minD + D;
   const int P1 = prm->P1 > 0 ? prm->P1 : 2;
@@ -69,6 +79,7 @@ int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, in
   const int INVALID = (minD - 1) * 16;
   const int mode = prm->mode;
   if (D <= 0 || D % 16 != 0 || D > 1024) return -2;
+  if (cn != 1 && cn != 3) return -2;
   if (mode != SVO_MODE_SGBM && mode != SVO_MODE_HH && mode != SVO_MODE_HH4) return -2;
   /* cv2 raises for MODE_SGBM / MODE_HH when width - (minD + D) <= blockSize/2; MODE_HH4 does not */
   if (mode != SVO_MODE_HH4 && W - (minD + D) <= bs / 2) return -2;
@@ -84,31 +95,33 @@ int svo_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H, in
   uint8_t *gL = buf, *iL = buf + npix, *gR = buf + 2 * npix, *iR = buf + 3 * npix;
   uint8_t *lo[4], *hi[4];
   for (int k = 0; k < 4; k++) { lo[k] = buf + (4 + k) * npix; hi[k] = buf + (8 + k) * npix; }
-  prefilter(left, W, H, lstride, ftzero, gL, iL);
-  prefilter(right, W, H, rstride, ftzero, gR, iR);
-  for (int y = 0; y < H; y++) {
-    size_t o = (size_t)y * W;
-    lohi(gL + o, W, lo[0] + o, hi[0] + o); lohi(iL + o, W, lo[1] + o, hi[1] + o);
-    lohi(gR + o, W, lo[2] + o, hi[2] + o); lohi(iR + o, W, lo[3] + o, hi[3] + o);
-  }
 
   const size_t ncell = (size_t)W1 * H * D;
-  uint16_t* pix = (uint16_t*)malloc(ncell * 2);
+  uint16_t* pix = (uint16_t*)calloc(ncell, 2);
   int16_t* C = (int16_t*)malloc(ncell * 2);
   int16_t* S = (int16_t*)calloc(ncell, 2);
-  /* A.3 pixel cost */
-  for (int y = 0; y < H; y++)
-    for (int xp = 0; xp < W1; xp++) {
-      const int x = xp + minX1;
-      const size_t o = (size_t)y * W;
-      uint16_t* pp = pix + ((size_t)y * W1 + xp) * D;
-      for (int d = 0; d < D; d++) {
-        const int xr = x - (d + minD);
-        int cg = bt(gL[o + x], gR[o + xr], lo[0][o + x], hi[0][o + x], lo[2][o + xr], hi[2][o + xr]);
-        int ci = bt(iL[o + x], iR[o + xr], lo[1][o + x], hi[1][o + x], lo[3][o + xr], hi[3][o + xr]);
-        pp[d] = (uint16_t)(cg + (ci >> 2));
-      }
+  for (int ch = 0; ch < cn; ch++) {
+    prefilter(left + ch, W, H, lstride, cn, ftzero, gL, iL);
+    prefilter(right + ch, W, H, rstride, cn, ftzero, gR, iR);
+    for (int y = 0; y < H; y++) {
+      size_t o = (size_t)y * W;
+      lohi(gL + o, W, lo[0] + o, hi[0] + o); lohi(iL + o, W, lo[1] + o, hi[1] + o);
+      lohi(gR + o, W, lo[2] + o, hi[2] + o); lohi(iR + o, W, lo[3] + o, hi[3] + o);
     }
+    /* A.3 pixel cost, accumulated over the channels */
+    for (int y = 0; y < H; y++)
+      for (int xp = 0; xp < W1; xp++) {
+        const int x = xp + minX1;
+        const size_t o = (size_t)y * W;
+        uint16_t* pp = pix + ((size_t)y * W1 + xp) * D;
+        for (int d = 0; d < D; d++) {
+          const int xr = x - (d + minD);
+          int cg = bt(gL[o + x], gR[o + xr], lo[0][o + x], hi[0][o + x], lo[2][o + xr], hi[2][o + xr]);
+          int ci = bt(iL[o + x], iR[o + xr], lo[1][o + x], hi[1][o + x], lo[3][o + xr], hi[3][o + xr]);
+          pp[d] = (uint16_t)(pp[d] + cg + (ci >> 2));
+        }
+      }
+  }
   /* A.4 block sum, clamped in W1 coordinates; stored C = Ctrue + P2 (int16) */
   /* (separable: horizontal window sums first, then vertical) */
   uint16_t* hs = (uint16_t*)malloc(ncell * 2);

@@ -210,6 +210,32 @@ def save_bottle(path):
           "post sha", hashlib.sha256(post.tobytes()).hexdigest()[:16], "valid", float((raw >= 0).mean()))
 
 
+def save_sgbm3(path):
+    """cv2.StereoSGBM on 8UC3 pairs (the cost is summed over the three channels), all three modes."""
+    out = {}
+    n = 0
+    rng = np.random.default_rng(4321)
+    for (H, W, D, bs, minD) in [(40, 150, 32, 5, 0), (33, 120, 16, 3, 0), (50, 200, 64, 7, 4), (30, 140, 48, 5, -8), (37, 300, 224, 3, 0)]:
+        for mode in (cv2.STEREO_SGBM_MODE_SGBM, cv2.STEREO_SGBM_MODE_HH, cv2.STEREO_SGBM_MODE_HH4):
+            for kind in ("synth", "noise"):
+                if kind == "synth":
+                    l1, r1 = synth_pair(H, W, D, seed=H)
+                    l = np.stack([l1, np.roll(l1, 1, axis=0) // 2 + 30, 255 - l1], axis=2).astype(np.uint8)
+                    r = np.stack([r1, np.roll(r1, 1, axis=0) // 2 + 30, 255 - r1], axis=2).astype(np.uint8)
+                else:
+                    l = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+                    r = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+                k = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=8 * bs * bs, P2=32 * bs * bs, disp12MaxDiff=1, preFilterCap=31,
+                         uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=mode)
+                out[f"l{n}"], out[f"r{n}"], out[f"d{n}"] = l, r, cv_sgbm(l, r, k)
+                out[f"p{n}"] = np.array([k[x] for x in ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
+                                                        "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")], np.int32)
+                n += 1
+    out["n"] = np.array(n)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes", n, "cases")
+
+
 def save_bm_mind(path):
     """cv2.StereoBM with minDisparity != 0.  OpenCV indexes past the end of the image rows there, so only the pixels
     inside cv::getValidDisparityROI are reproducible; the ROI (y0, y1, x0, x1) is stored with every case."""
@@ -266,7 +292,7 @@ def save_rectify(path):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind)
+    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))

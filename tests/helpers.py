@@ -44,3 +44,10 @@ def bm_mind_golden_cases():
     g = golden("bm_mind_small")
     for i in range(int(g["n"])):
         yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(BM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"], tuple(int(v) for v in g[f"roi{i}"])
+
+
+def sgbm3_golden_cases():
+    """StereoSGBM on 8UC3 pairs: (index, left, right, params, cv2 disparity)."""
+    g = golden("sgbm3_small")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]

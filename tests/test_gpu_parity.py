@@ -28,6 +28,22 @@ def test_sgbm_golden_all_modes(svgpu):
             assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
 
 
+def test_sgbm_three_channel_golden(svgpu, oracle):
+    """cv::StereoSGBM::compute on 8UC3 pairs (svgpu_pipeline with SV_STAGE_SGBM alone): bit-exact against cv2's output; a
+    block size whose three-channel cost could leave the 16-bit range is refused."""
+    from helpers import sgbm3_golden_cases
+    for i, l, r, prm, want in sgbm3_golden_cases():
+        with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
+            ctx.set_sgbm(**prm)
+            assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
+    l = np.zeros((40, 200, 3), np.uint8)
+    with svgpu.Context(200, 40) as ctx:
+        ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=11, P1=8, P2=32, mode=1))
+        with pytest.raises(svgpu.SvgpuError) as e:
+            ctx.sgbm(l, l)
+        assert e.value.code == svgpu._abi.SV_INVALID_SETTINGS
+
+
 def test_sgbm_too_narrow_matches_reference_error(svgpu):
     l = np.zeros((21, 40), np.uint8)
     with svgpu.Context(40, 21) as ctx:

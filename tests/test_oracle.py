@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm_golden_cases
+from helpers import bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm3_golden_cases, sgbm_golden_cases
 
 
 def test_sgbm_golden(oracle):
@@ -15,6 +15,15 @@ def test_sgbm_golden(oracle):
         assert nmismatch(got, want) == 0, (i, prm)
         n += 1
     assert n > 100
+
+
+def test_sgbm_three_channel_golden(oracle):
+    """8UC3 input (not what the reference passes, but part of cv::StereoSGBM::compute): cost summed over the channels."""
+    n = 0
+    for i, l, r, prm, want in sgbm3_golden_cases():
+        assert nmismatch(oracle.sgbm(l, r, **prm), want) == 0, (i, prm)
+        n += 1
+    assert n == 30
 
 
 def test_sgbm_too_narrow_is_an_error(oracle):
