@@ -52,6 +52,136 @@ static inline int bt(int u, int v, int loL, int hiL, int loR, int hiR) {
   return imin(c0, c1);
 }
 
+/* A.6 for one image row: winner-take-all + uniqueness + sub-pixel over S[x'][d], then the left-right check; writes the
+ * row `dr` (W values, INVALID where nothing is selected).  disp2 / disp2cost are scratch rows of W entries. */
+static void wta_lr_row(const int16_t* Srow, int W, int W1, int D, int minD, int minX1, int maxX1, int uniq, int d12, int INVALID,
+                       int simd8, int16_t* disp2, int* disp2cost, int16_t* dr) {
+  for (int x = 0; x < W; x++) { disp2[x] = (int16_t)INVALID; disp2cost[x] = MAXC; }
+  for (int xp = W1 - 1; xp >= 0; xp--) {
+    const int16_t* sp = Srow + (size_t)xp * D;
+    int minS = MAXC, best = -1;
+    for (int d = 0; d < D; d++)
+      if (sp[d] < minS) { minS = sp[d]; best = d; }
+    if (best < 0 && !simd8) continue; /* all saturated */
+    int d;
+    if (simd8) {
+      /* computeDisparity3WAY selects the winner with 8-lane vector code: every lane (d mod 8) keeps the LAST disparity
+       * that attains the minimum, the lanes are then reduced to the smallest such disparity; and its uniqueness test
+       * compares against (short)(100*minS/(100-uniq) + 1) instead of cross-multiplying. */
+      if (best < 0) { minS = MAXC; }
+      best = -1;
+      for (int j = 0; j < 8 && j < D; j++) {
+        int last = -1;
+        for (int k = j; k < D; k += 8)
+          if (sp[k] == minS) last = k;
+        if (last >= 0 && (best < 0 || last < best)) best = last;
+      }
+      if (uniq > 0) {
+        const int16_t thr = (int16_t)(uint16_t)((100 * minS) / (100 - uniq) + 1);
+        for (d = 0; d < D; d++)
+          if (sp[d] < thr && abs(best - d) > 1) break;
+        if (d < D) continue;
+      }
+    } else {
+      for (d = 0; d < D; d++)
+        if (sp[d] * (100 - uniq) < minS * 100 && abs(best - d) > 1) break;
+      if (d < D) continue;
+    }
+    const int x2 = xp + minX1 - best - minD;
+    if (disp2cost[x2] > minS) { disp2cost[x2] = minS; disp2[x2] = (int16_t)(best + minD); }
+    int dfix;
+    if (0 < best && best < D - 1) {
+      int den = imax(sp[best - 1] + sp[best + 1] - 2 * sp[best], 1);
+      dfix = best * 16 + ((sp[best - 1] - sp[best + 1]) * 16 + den) / (den * 2);
+    } else
+      dfix = best * 16;
+    dr[xp + minX1] = (int16_t)(dfix + minD * 16);
+  }
+  for (int x = minX1; x < maxX1; x++) {
+    const int d1 = dr[x];
+    if (d1 == INVALID) continue;
+    const int _d = d1 >> 4, d_ = (d1 + 15) >> 4, _x = x - _d, x_ = x - d_;
+    if (0 <= _x && _x < W && disp2[_x] >= minD && abs(disp2[_x] - _d) > d12 &&
+        0 <= x_ && x_ < W && disp2[x_] >= minD && abs(disp2[x_] - d_) > d12)
+      dr[x] = (int16_t)INVALID;
+  }
+}
+
+/* one min-plus step of a path (A.5): L(p,.) from L(q,.) of the predecessor (q == NULL: outside, L = 0) */
+static void path_step(const int16_t* lq, const int16_t* c /* Ctrue */, int D, int P1, int P2, int16_t* out) {
+  int m = 0;
+  if (lq) { m = MAXC; for (int d = 0; d < D; d++) m = imin(m, lq[d]); }
+  for (int d = 0; d < D; d++) {
+    const int a = lq ? lq[d] : 0;
+    const int b = (lq ? (d > 0 ? lq[d - 1] : MAXC) : 0) + P1;
+    const int e = (lq ? (d < D - 1 ? lq[d + 1] : MAXC) : 0) + P1;
+    const int v = c[d] + imin(imin(a, b), imin(e, m + P2)) - m;
+    out[d] = (int16_t)(v > MAXC ? MAXC : v);
+  }
+}
+
+/* MODE_SGBM_3WAY (OpenCV's computeDisparity3WAY; black-box restatement pinned against cv2 4.13, tests/golden/sgbm3way_small.npz):
+ *  - the image is cut into 4 stripes of ceil(H/4) rows, each processed on its own from `overlap` rows above its first row
+ *    (overlap = blockSize/2 + 1 + ceil(0.1 * stripe rows)); the vertical path restarts at the first processed row;
+ *  - block sums take the rows above the first processed row of a stripe from that row (clamp) but real image rows below
+ *    the stripe;
+ *  - per row: path left-to-right and path top-down in one pass, path right-to-left in a second pass, S = sum of the three,
+ *    then the usual winner-take-all / uniqueness / sub-pixel / left-right check of the row;
+ *  - every stripe writes into a private buffer of (stripe rows + overlap) rows at row offset `overlap` (stripe 0) or 0,
+ *    and buffer rows [overlap, ..) become the stripe's image rows: for images so small that a stripe's overlap would
+ *    start above row 0 the rows are therefore shifted, exactly as OpenCV produces them. */
+static void sgbm_3way(const uint16_t* hs, int W, int H, int W1, int D, int minD, int minX1, int maxX1, int SH2, int P1, int P2, int uniq,
+                      int d12, int INVALID, int16_t* disp, int dstride) {
+  const int nstripes = 4;
+  const int sz = (H + nstripes - 1) / nstripes;
+  const int ov = (SH2 + 1) + (sz + 9) / 10; /* ceil(0.1 * sz) */
+  const size_t rowCells = (size_t)W1 * D;
+  int16_t* Ctrue = (int16_t*)malloc(rowCells * 2);
+  int16_t* Ll = (int16_t*)malloc(rowCells * 2);
+  int16_t* Lv = (int16_t*)malloc(rowCells * 2);
+  int16_t* Srow = (int16_t*)malloc(rowCells * 2);
+  int16_t* buf = (int16_t*)malloc((size_t)(sz + ov) * W * 2);
+  int16_t* disp2 = (int16_t*)malloc((size_t)W * 2);
+  int* disp2cost = (int*)malloc((size_t)W * sizeof(int));
+  int16_t Lr[2][1024];
+  for (int s = 0; s < nstripes; s++) {
+    const int start = imax(imin(s * sz - ov, H), 0), end = imin((s + 1) * sz, H);
+    if (end <= start) continue;
+    const int dstOff = s == 0 ? ov : 0;
+    for (size_t i = 0; i < (size_t)(sz + ov) * W; i++) buf[i] = (int16_t)INVALID;
+    for (int y = 0; y < end - start; y++) {
+      for (int xp = 0; xp < W1; xp++) {
+        int acc[1024];
+        for (int d = 0; d < D; d++) acc[d] = 0;
+        for (int dy = -SH2; dy <= SH2; dy++) {
+          const uint16_t* hp = hs + ((size_t)iclamp(start + y + dy, start, H - 1) * W1 + xp) * D;
+          for (int d = 0; d < D; d++) acc[d] += hp[d];
+        }
+        for (int d = 0; d < D; d++) Ctrue[(size_t)xp * D + d] = (int16_t)acc[d];
+      }
+      for (int xp = 0; xp < W1; xp++) {
+        path_step(xp > 0 ? Ll + (size_t)(xp - 1) * D : NULL, Ctrue + (size_t)xp * D, D, P1, P2, Ll + (size_t)xp * D);
+        int16_t tmp[1024];
+        path_step(y > 0 ? Lv + (size_t)xp * D : NULL, Ctrue + (size_t)xp * D, D, P1, P2, tmp);
+        memcpy(Lv + (size_t)xp * D, tmp, (size_t)D * 2);
+      }
+      for (int xp = W1 - 1; xp >= 0; xp--) {
+        int16_t* cur = Lr[xp & 1];
+        path_step(xp < W1 - 1 ? Lr[(xp + 1) & 1] : NULL, Ctrue + (size_t)xp * D, D, P1, P2, cur);
+        for (int d = 0; d < D; d++) {
+          const int v = Ll[(size_t)xp * D + d] + Lv[(size_t)xp * D + d] + cur[d];
+          Srow[(size_t)xp * D + d] = (int16_t)(v > MAXC ? MAXC : v);
+        }
+      }
+      if (dstOff + y < sz + ov)
+        wta_lr_row(Srow, W, W1, D, minD, minX1, maxX1, uniq, d12, INVALID, 1, disp2, disp2cost, buf + (size_t)(dstOff + y) * W);
+    }
+    for (int k = 0; s * sz + k < imin((s + 1) * sz, H); k++)
+      memcpy((uint8_t*)disp + (size_t)(s * sz + k) * dstride, buf + (size_t)(ov + k) * W, (size_t)W * 2);
+  }
+  free(Ctrue); free(Ll); free(Lv); free(Srow); free(buf); free(disp2); free(disp2cost);
+}
+
 /* test hooks: when non-NULL the oracle copies its cost volume Ctrue (= C - P2) and the aggregated S
  * ([y][x'][d], int16) here so that GPU intermediates can be diffed stage by stage */
 int16_t* svo_debug_C = 0;
@@ -80,7 +210,9 @@ int svo_sgbm_compute_cn(const uint8_t* left, const uint8_t* right, int W, int H,
   const int mode = prm->mode;
   if (D <= 0 || D % 16 != 0 || D > 1024) return -2;
   if (cn != 1 && cn != 3) return -2;
-  if (mode != SVO_MODE_SGBM && mode != SVO_MODE_HH && mode != SVO_MODE_HH4) return -2;
+  /* OpenCV's 3WAY uniqueness test divides by (100 - uniquenessRatio): cv2 dies with SIGFPE at 100 */
+  if (mode == SVO_MODE_SGBM_3WAY && uniq >= 100) return -2;
+  if (mode != SVO_MODE_SGBM && mode != SVO_MODE_HH && mode != SVO_MODE_HH4 && mode != SVO_MODE_SGBM_3WAY) return -2;
   /* cv2 raises for MODE_SGBM / MODE_HH when width - (minD + D) <= blockSize/2; MODE_HH4 does not */
   if (mode != SVO_MODE_HH4 && W - (minD + D) <= bs / 2) return -2;
 
@@ -134,6 +266,11 @@ int svo_sgbm_compute_cn(const uint8_t* left, const uint8_t* right, int W, int H,
         for (int d = 0; d < D; d++) hp[d] = (uint16_t)(hp[d] + pp[d]);
       }
     }
+  if (mode == SVO_MODE_SGBM_3WAY) {
+    sgbm_3way(hs, W, H, W1, D, minD, minX1, maxX1, SH2, P1, P2, uniq, d12, INVALID, disp, dstride);
+    free(hs); free(pix); free(buf); free(C); free(S);
+    goto median;
+  }
   for (int y = 0; y < H; y++)
     for (int xp = 0; xp < W1; xp++) {
       int16_t* cp = C + ((size_t)y * W1 + xp) * D;
@@ -240,6 +377,7 @@ int svo_sgbm_compute_cn(const uint8_t* left, const uint8_t* right, int W, int H,
   free(disp2cost);
   free(S);
 
+median:;
   /* A.7 median 3x3 in place, then the built-in speckle stage */
   int16_t* tmpi = (int16_t*)malloc(npix * 2);
   int16_t* tmpo = (int16_t*)malloc(npix * 2);

@@ -236,6 +236,33 @@ def save_sgbm3(path):
     print("wrote", path, os.path.getsize(path), "bytes", n, "cases")
 
 
+def save_sgbm3way(path):
+    """cv2.StereoSGBM MODE_SGBM_3WAY: textured and noise pairs (noise exercises the tie-breaking of OpenCV's vectorised
+    winner search and its uniqueness threshold), images smaller than the stripe overlap, minDisparity of both signs."""
+    out = {}
+    n = 0
+    rng = np.random.default_rng(99)
+    for (H, W, D, P1, P2, uniq, bs, minD, d12) in [(64, 160, 32, 200, 800, 10, 5, 0, 1), (57, 180, 64, 392, 1568, 15, 7, 0, 1), (41, 150, 16, 8, 32, 10, 3, 0, 1),
+                                                   (50, 170, 32, 100, 400, 10, 5, 5, 1), (50, 170, 32, 100, 400, 10, 5, -6, 2), (9, 120, 16, 100, 400, 10, 5, 0, 1),
+                                                   (3, 120, 16, 100, 400, 10, 3, 0, 1), (17, 120, 16, 100, 400, 10, 11, 0, 1), (40, 140, 32, 2, 5, 5, 1, 0, 1),
+                                                   (40, 140, 32, 100, 400, 99, 5, 0, 1), (40, 330, 224, 392, 1568, 15, 7, 0, 1), (48, 240, 128, 72, 288, 0, 3, 0, 100)]:
+        for kind in ("synth", "noise"):
+            if kind == "synth":
+                l, r = synth_pair(H, W, max(D + minD, 8), seed=H + D)
+            else:
+                l = rng.integers(0, 256, (H, W), dtype=np.uint8)
+                r = rng.integers(0, 256, (H, W), dtype=np.uint8)
+            k = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=d12, preFilterCap=31,
+                     uniquenessRatio=uniq, speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_SGBM_3WAY)
+            out[f"l{n}"], out[f"r{n}"], out[f"d{n}"] = l, r, cv_sgbm(l, r, k)
+            out[f"p{n}"] = np.array([k[x] for x in ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
+                                                    "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")], np.int32)
+            n += 1
+    out["n"] = np.array(n)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes", n, "cases")
+
+
 def save_bm_mind(path):
     """cv2.StereoBM with minDisparity != 0.  OpenCV indexes past the end of the image rows there, so only the pixels
     inside cv::getValidDisparityROI are reproducible; the ROI (y0, y1, x0, x1) is stored with every case."""
@@ -292,7 +319,7 @@ def save_rectify(path):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3)
+    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))

@@ -51,3 +51,10 @@ def sgbm3_golden_cases():
     g = golden("sgbm3_small")
     for i in range(int(g["n"])):
         yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]
+
+
+def sgbm3way_golden_cases():
+    """MODE_SGBM_3WAY: (index, left, right, params, cv2 disparity)."""
+    g = golden("sgbm3way_small")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]

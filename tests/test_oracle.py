@@ -5,7 +5,8 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm3_golden_cases, sgbm_golden_cases
+from helpers import (bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm3_golden_cases, sgbm3way_golden_cases,
+                     sgbm_golden_cases)
 
 
 def test_sgbm_golden(oracle):
@@ -24,6 +25,19 @@ def test_sgbm_three_channel_golden(oracle):
         assert nmismatch(oracle.sgbm(l, r, **prm), want) == 0, (i, prm)
         n += 1
     assert n == 30
+
+
+def test_sgbm_3way_golden(oracle):
+    """MODE_SGBM_3WAY (OpenCV's computeDisparity3WAY), restated from its observable behaviour: four stripes with restarted
+    vertical paths, the vectorised winner search's tie rule and uniqueness threshold, the stripe-buffer row offsets of tiny
+    images.  Bit-exact on every golden case; uniquenessRatio = 100 is an error (cv2 itself dies with SIGFPE there)."""
+    n = 0
+    for i, l, r, prm, want in sgbm3way_golden_cases():
+        assert nmismatch(oracle.sgbm(l, r, **prm), want) == 0, (i, prm)
+        n += 1
+    assert n == 24
+    with pytest.raises(ValueError):
+        oracle.sgbm(l, r, **dict(prm, uniquenessRatio=100))
 
 
 def test_sgbm_too_narrow_is_an_error(oracle):
@@ -113,7 +127,7 @@ def test_live_cv2_random(oracle, cv2):
         prm = dict(minDisparity=int(rng.choice([0, 0, 3, -5])), numDisparities=D, blockSize=bs, P1=8 * bs * bs,
                    P2=32 * bs * bs, disp12MaxDiff=int(rng.choice([1, 2])), preFilterCap=int(rng.integers(5, 64)),
                    uniquenessRatio=int(rng.integers(0, 20)), speckleWindowSize=0, speckleRange=0,
-                   mode=int(rng.choice([0, 1, 3])))
+                   mode=int(rng.choice([0, 1, 2, 3])))
         s = cv2.StereoSGBM_create(**prm)
         assert nmismatch(oracle.sgbm(l, r, **prm), s.compute(l, r)) == 0, prm
         d = s.compute(l, r)
