@@ -102,7 +102,14 @@ int check_status(svgpu_ctx* c) {
 
 int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   const SgbmCfg& g = c->cfg;
-  const size_t cells = g.W1 > 0 ? (size_t)g.W1 * g.H * g.D : 0;
+  // MODE_SGBM_3WAY works on four stripe frames per pair (common.cuh: StripeGeom): volumes, selection and the sweep's
+  // hand-over buffers are sized for 4 x batch frames of Hs rows, plus one extra full-size disparity plane per pair
+  const bool way3 = g.mode == SV_MODE_SGBM_3WAY;
+  const int vrows = sgbm_volume_rows(g);
+  SgbmCfg gs = g;
+  if (way3) gs.H = vrows / 4;
+  const int sweepFrames = way3 ? batch * 4 : batch;
+  const size_t cells = g.W1 > 0 ? (size_t)g.W1 * vrows * g.D : 0;
   if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->allocCn >= cn && c->sc.dispRaw) return SV_OK;
   batch = std::max(batch, c->allocBatch);
   cn = std::max(cn, c->allocCn);
@@ -115,15 +122,15 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   A((void**)&c->sc.planesR, planeBytes);
   A((void**)&c->sc.C, (size_t)batch * cells * 2);
   A((void**)&c->sc.S, (size_t)batch * cells * 2);
-  A((void**)&c->sc.sel, (size_t)batch * g.H * w1 * 8);
-  A((void**)&c->sc.dispRaw, (size_t)batch * g.H * g.W * 2);
+  A((void**)&c->sc.sel, (size_t)batch * vrows * w1 * 8);
+  A((void**)&c->sc.dispRaw, (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2);
   A((void**)&c->sc.status, 256);
-  A((void**)&c->sc.flags, sgbm_flags_bytes(g, batch));
-  A((void**)&c->sc.edges, sgbm_edges_bytes(g, batch));
+  A((void**)&c->sc.flags, sgbm_flags_bytes(gs, sweepFrames));
+  A((void**)&c->sc.edges, sgbm_edges_bytes(gs, sweepFrames));
   if (e != cudaSuccess) { free_scratch(c); return cuda_fail(c, e, "cudaMalloc(sgbm scratch)"); }
   cudaMemsetAsync(c->sc.status, 0, 256, c->st);
-  cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(g, batch), c->st);
-  cudaMemsetAsync(c->sc.edges, 0, sgbm_edges_bytes(g, batch), c->st);  // launch tags start at 1
+  cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(gs, sweepFrames), c->st);
+  cudaMemsetAsync(c->sc.edges, 0, sgbm_edges_bytes(gs, sweepFrames), c->st);  // launch tags start at 1
   c->sc.frameCells = cells;
   c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp; c->allocCn = cn;
   return SV_OK;
@@ -133,7 +140,8 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
 int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
   if (p.numDisparities <= 0 || p.numDisparities % 16 != 0) return fail(c, SV_INVALID_SETTINGS, "numDisparities must be a positive multiple of 16");
   if (p.numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported");
-  if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4) return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH or MODE_HH4");
+  if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4 && p.mode != SV_MODE_SGBM_3WAY)
+    return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH, MODE_SGBM_3WAY or MODE_HH4");
   if (p.blockSize > 11 || (p.blockSize > 0 && p.blockSize % 2 == 0)) return fail(c, SV_INVALID_SETTINGS, "blockSize must be odd and <= 11");
   if (p.preFilterCap > 63) return fail(c, SV_INVALID_SETTINGS, "preFilterCap must be <= 63");
   g.W = c->W; g.H = c->H;
@@ -154,6 +162,8 @@ int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
   g.speckleWindowSize = p.speckleWindowSize;
   g.speckleRange = p.speckleRange;
   if (g.uniq > 100) return fail(c, SV_INVALID_SETTINGS, "uniquenessRatio must be <= 100");
+  // OpenCV's MODE_SGBM_3WAY divides by (100 - uniquenessRatio)
+  if (g.mode == SV_MODE_SGBM_3WAY && g.uniq >= 100) return fail(c, SV_INVALID_SETTINGS, "uniquenessRatio must be < 100 in MODE_SGBM_3WAY");
   // 16-bit headroom: every path cost L <= Ctrue + P2 must stay below MAX_COST, as in OpenCV's own contract
   const long long maxC = (long long)bs * bs * (2 * g.ftzero + 63);
   if (maxC + g.P2 > 32767) return fail(c, SV_INVALID_SETTINGS, "blockSize^2*(2*ftzero+63) + P2 exceeds the 16-bit cost range");

@@ -46,6 +46,32 @@ struct SgbmScratch {
   size_t frameCells;  // W1*H*D
 };
 
+// MODE_SGBM_3WAY (OpenCV's computeDisparity3WAY; restated in oracle/sv_oracle_sgbm.c: sgbm_3way) cuts the image into four
+// stripes of ceil(H/4) rows; stripe s is processed as an image of its own from `ov` rows above its first row ("stripe frame",
+// rows[s] rows, padded to Hs).  Its result row y lands in row dstOff[s] + y of a private buffer whose rows [ov, ..) become the
+// image rows [s*sz, ..): image row s*sz + k therefore comes from stripe row ov + k - dstOff[s].
+struct StripeGeom {
+  int sz, ov, Hs;
+  int start[4], rows[4], dstOff[4];
+};
+inline StripeGeom stripe_geom(int H, int r) {
+  StripeGeom g;
+  g.sz = (H + 3) / 4;
+  g.ov = (r + 1) + (g.sz + 9) / 10;
+  g.Hs = 1;
+  for (int s = 0; s < 4; s++) {
+    const int a = s * g.sz - g.ov;
+    g.start[s] = a > H ? H : (a < 0 ? 0 : a);
+    const int e = (s + 1) * g.sz < H ? (s + 1) * g.sz : H;
+    g.rows[s] = e > g.start[s] ? e - g.start[s] : 0;
+    g.dstOff[s] = s == 0 ? g.ov : 0;
+    if (g.rows[s] > g.Hs) g.Hs = g.rows[s];
+  }
+  return g;
+}
+// rows of volume / selection storage one pair needs
+inline int sgbm_volume_rows(const SgbmCfg& cfg) { return cfg.mode == 2 /* SV_MODE_SGBM_3WAY */ ? 4 * stripe_geom(cfg.H, cfg.r).Hs : cfg.H; }
+
 struct LaunchStats {
   long long launches = 0;
 };
@@ -55,7 +81,16 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
                          size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS, int cn = 1);
 // sgbm_cost.cu: Birchfield-Tomasi pixel cost + box sum -> cost volume
-cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int cn, cudaStream_t st);
+// what one launch of the cost kernel reads and writes: `nframes` frames of `rowsOut` rows each; cfg.H is the row at which the
+// vertical window clamps (>= rowsOut), planeRows the rows per frame of the operand planes, frameCells the cells per frame of C
+struct CostView {
+  const uint8_t* planesL;
+  const uint8_t* planesR;
+  uint16_t* C;
+  size_t frameCells;
+  int planeRows, rowsOut;
+};
+cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& view, int nframes, int cn, cudaStream_t st);
 // sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats);

@@ -131,6 +131,18 @@ __global__ void k_fill_rows_s16(int16_t* p, size_t stride, size_t frame, int W, 
   if (x < W) *(int16_t*)((uint8_t*)p + blockIdx.z * frame + (size_t)y * stride + (size_t)x * 2) = (int16_t)v;
 }
 
+// MODE_SGBM_3WAY: assemble the image from the rows of its four stripe frames (common.cuh: StripeGeom)
+__global__ void __launch_bounds__(256) k_gather_stripes(const int16_t* __restrict__ stripes, int16_t* __restrict__ full, int W, int H,
+                                                        StripeGeom g, int invalid) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y, pair = blockIdx.z;
+  if (x >= W) return;
+  const int s = min(yy / g.sz, 3), k = yy - s * g.sz;
+  const int y = g.ov + k - g.dstOff[s];
+  int v = invalid;
+  if (y >= 0 && y < g.rows[s]) v = stripes[(((size_t)pair * 4 + s) * g.Hs + y) * W + x];
+  full[((size_t)pair * H + yy) * W + x] = (int16_t)v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +167,47 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
                                           cfg.Wp, cn, cfg.ftzero);
     SV_LAUNCHED();
   }
-  SV_RET(sgbm_cost_volume(cfg, sc, nframes, cn, st));
+  if (cfg.mode == SV_MODE_SGBM_3WAY) {
+    const StripeGeom g = stripe_geom(H, cfg.r);
+    SgbmCfg cs = cfg;   // a stripe frame
+    cs.H = g.Hs;
+    const size_t cellsStripe = (size_t)cfg.W1 * g.Hs * cfg.D;
+    const size_t planeRowBytes = (size_t)2 * cn * cfg.Wp * sizeof(uint2);
+    // rows of a stripe frame below its stripe are never produced: keep them defined
+    SV_RET(cudaMemsetAsync(sc.C, 0, (size_t)nframes * 4 * cellsStripe * 2, st));
+    for (int s = 0; s < 4; s++) {
+      if (g.rows[s] <= 0) continue;
+      SgbmCfg cc = cfg;
+      cc.H = H - g.start[s];  // block sums clamp at the first row of the stripe frame, and at the last image row
+      const CostView v{sc.planesL + g.start[s] * planeRowBytes, sc.planesR + g.start[s] * planeRowBytes, sc.C + s * cellsStripe,
+                       4 * cellsStripe, H, g.rows[s]};
+      SV_RET(sgbm_cost_volume(cc, v, nframes, cn, st));
+      if (stats) stats->launches++;
+    }
+    if (ev) SV_RET(cudaEventRecord(ev[1], st));
+    SgbmScratch ss = sc;
+    ss.frameCells = cellsStripe;
+    SV_RET(sgbm_aggregate_sweep(cs, ss, nframes * 4, 0, st, stats));
+    if (ev) SV_RET(cudaEventRecord(ev[2], st));
+    int16_t* dispStripes = sc.dispRaw;
+    int16_t* dispFull = sc.dispRaw + (size_t)nframes * 4 * g.Hs * W;
+    {
+      dim3 gs(g.Hs, nframes * 4);
+      k_select_lr<<<gs, 256, (size_t)W * 6, st>>>(sc.sel, dispStripes, cs);
+      SV_LAUNCHED();
+      dim3 gg((W + 255) / 256, H, nframes);
+      k_gather_stripes<<<gg, 256, 0, st>>>(dispStripes, dispFull, W, H, g, cfg.invalid);
+      SV_LAUNCHED();
+      SV_RET(launch_median3(dispFull, (size_t)W * 2, disp, dstride, W, H, nframes, (size_t)W * H * 2, dframe, st));
+      if (stats) stats->launches++;
+    }
+    if (ev) SV_RET(cudaEventRecord(ev[3], st));
+    return cudaSuccess;
+  }
+  {
+    const CostView v{sc.planesL, sc.planesR, sc.C, sc.frameCells, H, H};
+    SV_RET(sgbm_cost_volume(cfg, v, nframes, cn, st));
+  }
   if (stats) stats->launches++;
   if (ev) SV_RET(cudaEventRecord(ev[1], st));
   SV_RET(sgbm_aggregate_sweep(cfg, sc, nframes, debugS, st, stats));

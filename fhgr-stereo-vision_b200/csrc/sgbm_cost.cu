@@ -63,7 +63,8 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
 // so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
 template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
 __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
-                                                                uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4) {
+                                                                uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4,
+                                                                int planeRows, int rowsOut) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
   extern __shared__ uint4 smemU4[];
   const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
@@ -76,9 +77,12 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
   const int tid = threadIdx.x, nthr = blockDim.x;  // nthr = NCP * ng
   const int frame = blockIdx.z;
   const int x0 = blockIdx.x * TW;                  // first output column x' of the tile
-  const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, H);
-  const uint2* pL = planesL + (size_t)frame * H * CH * Wp;
-  const uint2* pR = planesR + (size_t)frame * H * CH * Wp;
+  // rows [0, rowsOut) of the frame are produced; the window clamps at rows 0 and H - 1 (H may exceed rowsOut: the stripe
+  // frames of MODE_SGBM_3WAY take the rows below them from the image); planeRows = rows per frame in the operand planes
+  const int yb = blockIdx.y * rowsPerBand, ye = min(yb + rowsPerBand, rowsOut);
+  if (yb >= ye) return;
+  const uint2* pL = planesL + (size_t)frame * planeRows * CH * Wp;
+  const uint2* pR = planesR + (size_t)frame * planeRows * CH * Wp;
   uint4* Cf = Cvol + (size_t)frame * frameU4;
 
   // ---- pixel-cost mapping: lanes = neighbouring column groups, thread = (COLS columns, 16 disparities)
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
 }
 
 template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
-cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
+cudaError_t launch_cost(const SgbmCfg& cfg, const CostView& v, int nframes, cudaStream_t st) {
   const CostGeom G = cost_geom<NC, RB, CH>(cfg.D);
   auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
@@ -273,26 +277,26 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, 
   const int tiles = (cfg.W1 + TW - 1) / TW;
   // bands: the CTA count should fill the 148 SMs (one CTA each) in whole waves, against the 2r-row run-in that every
   // extra band costs.  Estimated launch time in row steps = waves x (rows per band + run-in).
-  int bands = 1, rowsPerBand = cfg.H;
+  int bands = 1, rowsPerBand = (v.rowsOut + RB - 1) / RB * RB;
   {
     long long best = -1;
-    const int maxBands = std::max(1, std::min(16, (cfg.H + 63) / 64));
+    const int maxBands = std::max(1, std::min(16, (v.rowsOut + 63) / 64));
     for (int b = 1; b <= maxBands; b++) {
-      const int rpb = ((cfg.H + b - 1) / b + RB - 1) / RB * RB;
-      const int nb = (cfg.H + rpb - 1) / rpb;
+      const int rpb = ((v.rowsOut + b - 1) / b + RB - 1) / RB * RB;
+      const int nb = (v.rowsOut + rpb - 1) / rpb;
       const long long waves = ((long long)tiles * nframes * nb + 147) / 148;
       const long long cost = waves * (rpb + 2 * R + 4);
       if (best < 0 || cost < best) { best = cost; bands = nb; rowsPerBand = rpb; }
     }
   }
   dim3 grid(tiles, bands, nframes);
-  k<<<grid, (NC / COLS) * (cfg.D / kDPL), G.total, st>>>((const uint2*)sc.planesL, (const uint2*)sc.planesR, (uint4*)sc.C, cfg, rowsPerBand,
-                                                         sc.frameCells / 8);
+  k<<<grid, (NC / COLS) * (cfg.D / kDPL), G.total, st>>>((const uint2*)v.planesL, (const uint2*)v.planesR, (uint4*)v.C, cfg, rowsPerBand,
+                                                         v.frameCells / 8, v.planeRows, v.rowsOut);
   return cudaGetLastError();
 }
 
 template <int NC, int COLS, int RB, int ITEMS, int CH = 2>
-cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st) {
+cudaError_t launch_cost_r(const SgbmCfg& cfg, const CostView& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
     case 0: return launch_cost<0, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
     case 1: return launch_cost<1, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
@@ -306,7 +310,7 @@ cudaError_t launch_cost_r(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes
 }  // namespace
 
 // Ctrue of `nframes` pairs from their pre-filter planes
-cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int cn, cudaStream_t st) {
+cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes, int cn, cudaStream_t st) {
   // records staged per thread and row = (CH NC + CH NJ) / threads, CH = 2 planes per colour channel
   if (cn == 3) {
     if (cfg.D > 128) return launch_cost_r<32, 1, 8, 6, 6>(cfg, sc, nframes, st);

@@ -108,7 +108,11 @@ __device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& md
 // sum_d max(thr - S[d], 0) exceeds the shortfall of {best-1, best, best+1} iff another cell qualifies.
 // `scratch` holds the pixel's S so that the two neighbours of the winner can be looked up by index.
 // ------------------------------------------------------------------------------------------------
-template <int LPP>
+// WAY3 selects the semantics of OpenCV's MODE_SGBM_3WAY (oracle: wta_lr_row with simd8): among equal minima the winner is,
+// per residue class d mod 8, the LAST disparity, and among the classes the smallest of those; the uniqueness threshold is
+// (short)(100*minS/(100-uniq) + 1) instead of the cross-multiplied comparison (uniqMagic = ceil(2^32 / (100-uniq)) is then
+// used for a floor division).  Register i of a lane holds d0+i and d0+i+8, i.e. exactly one residue class.
+template <int LPP, bool WAY3 = false>
 __device__ __forceinline__ void sweep_wta(const uint32_t (&s)[kNR], uint16_t* scratch, int gl, bool active, int lane, int D,
                                           int uniqF, uint32_t uniqMagic, uint2& out) {
   const int d0 = gl * kDPL;
@@ -123,6 +127,23 @@ __device__ __forceinline__ void sweep_wta(const uint32_t (&s)[kNR], uint16_t* sc
     }
   }
   k = group_min_u32<LPP>(k, lane);
+  if constexpr (WAY3) {
+    // per residue class (= register) the largest disparity that attains the minimum, then the smallest over the classes
+    const uint32_t m = k >> 16;
+    uint32_t bestd = 0xFFFFu;
+#pragma unroll
+    for (int i = 0; i < kNR; i++) {
+      uint32_t c = 0;   // candidate + 1 (0: class has no minimum in this lane)
+      if (active) {
+        if ((s[i] & 0xFFFFu) == m) c = (uint32_t)(d0 + i + 1);
+        if ((s[i] >> 16) == m) c = (uint32_t)(d0 + i + 9);
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xFFFFFFFFu, c, o));
+      if (c) bestd = min(bestd, c - 1);
+    }
+    k = (m << 16) | bestd;
+  }
   const int minS = (int)(k >> 16), best = (int)(k & 0xFFFFu);
   // publish S of the pixel, look up the neighbours of the winner
   __syncwarp();
@@ -136,7 +157,13 @@ __device__ __forceinline__ void sweep_wta(const uint32_t (&s)[kNR], uint16_t* sc
   const int vp = best < D - 1 ? (int)scratch[vol_index(best + 1)] : 0;
   // shortfall against thr
   uint32_t thr;
-  {
+  if constexpr (WAY3) {
+    // floor(100*minS / uniqF) + 1, truncated to a signed 16-bit value; a negative threshold matches nothing.  uniqF = 100
+    // (uniquenessRatio 0) switches the test off.
+    uint32_t q = (uint32_t)minS * 100u / (uint32_t)max(uniqF, 1);
+    const int t16 = (int)(int16_t)(uint16_t)(q + 1u);
+    thr = (uniqF >= 100 || t16 <= 0) ? 0u : (uint32_t)t16;
+  } else {
     const uint32_t num = (uint32_t)minS * 100u + (uint32_t)uniqF - 1u;
     const uint32_t q = uniqF >= 2 ? __umulhi(num, uniqMagic) : (uniqF == 1 ? num : (minS ? 32768u : 0u));
     thr = min(q, 32768u);
@@ -149,7 +176,7 @@ __device__ __forceinline__ void sweep_wta(const uint32_t (&s)[kNR], uint16_t* sc
   }
   acc = group_sum_u32<LPP>(acc, lane);
   const int total = D * (int)thr - (int)acc;
-  int allowed = (int)thr - minS;
+  int allowed = max((int)thr - minS, 0);
   if (best > 0) allowed += max((int)thr - vm, 0);
   if (best < D - 1) allowed += max((int)thr - vp, 0);
   const uint32_t rej = total > allowed ? 0x80000000u : 0u;

@@ -193,7 +193,7 @@ __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int
   return true;
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW>
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
 __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_sweep(const SweepArgs a) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], sin[q], kMax2);
           uint2 o;
-          sweep_wta<LPP>(sum, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
+          sweep_wta<LPP, WAY3>(sum, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
           const unsigned off = (unsigned)yp * a.rowU4 + (unsigned)xp * (unsigned)a.pixU4;
           if (on && gl == 0) a.sel[((size_t)frame * H + yp) * W1 + xp] = o;
           if (a.debugS && on && active) {
@@ -606,23 +606,24 @@ int groups_of(const SgbmCfg& cfg, bool second, bool low) {
   return (smax_of(cfg) + 1 + spc - 1) / spc;
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW>
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
 cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
-  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW>;
+  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return e;
   k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int LPP, int PATHS, bool SECOND>
+template <int LPP, int PATHS, bool SECOND, bool WAY3 = false>
 cudaError_t launch_one(const SweepArgs& a, bool low, int grid, cudaStream_t st) {
-  return low ? launch_nw<LPP, PATHS, SECOND, kLowNW>(a, grid, st) : launch_nw<LPP, PATHS, SECOND, kMaxNW>(a, grid, st);
+  return low ? launch_nw<LPP, PATHS, SECOND, kLowNW, WAY3>(a, grid, st) : launch_nw<LPP, PATHS, SECOND, kMaxNW, WAY3>(a, grid, st);
 }
 
 template <int LPP>
-cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, bool low, int grid, cudaStream_t st) {
+cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, bool low, bool way3, int grid, cudaStream_t st) {
+  if (way3 && second) return launch_one<LPP, P_H, true, true>(a, low, grid, st);   // MODE_SGBM_3WAY: backward path + its selection rule
   if (!second) {
     if (paths == 15) return launch_one<LPP, 15, false>(a, low, grid, st);
     return launch_one<LPP, P_H | P_V, false>(a, low, grid, st);
@@ -667,7 +668,8 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.negp1dup = dup16((uint32_t)(-cfg.P1) & 0xFFFFu);
   a.uniqF = 100 - cfg.uniq;
   a.uniqMagic = a.uniqF >= 2 ? (uint32_t)((0x100000000ull + a.uniqF - 1) / a.uniqF) : 0u;
-  const int pass1 = cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : 15;
+  // MODE_SGBM_3WAY (on stripe frames, see sgbm.cu): left-to-right + top-down in pass 1, right-to-left in pass 2
+  const int pass1 = (cfg.mode == SV_MODE_HH4 || cfg.mode == SV_MODE_SGBM_3WAY) ? (P_H | P_V) : 15;
   const int pass2 = cfg.mode == SV_MODE_HH ? 15 : (cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : P_H);
   const int lpp = lpp_of(cfg.D);
   // SVGPU_SWEEP_NW=4|8 pins the variant (tests run every case through both)
@@ -684,11 +686,11 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
     const int paths = pass ? pass2 : pass1;
     const int grid = std::min(nframes * a.G, numSM);
     switch (lpp) {
-      case 1: e = launch_lpp<1>(a, paths, pass == 1, low, grid, st); break;
-      case 2: e = launch_lpp<2>(a, paths, pass == 1, low, grid, st); break;
-      case 4: e = launch_lpp<4>(a, paths, pass == 1, low, grid, st); break;
-      case 8: e = launch_lpp<8>(a, paths, pass == 1, low, grid, st); break;
-      default: e = launch_lpp<16>(a, paths, pass == 1, low, grid, st); break;
+      case 1: e = launch_lpp<1>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
+      case 2: e = launch_lpp<2>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
+      case 4: e = launch_lpp<4>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
+      case 8: e = launch_lpp<8>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
+      default: e = launch_lpp<16>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
     }
     if (stats) stats->launches++;
     if (e != cudaSuccess) return e;

@@ -55,7 +55,7 @@ enum {
 enum { SV_MEM_HOST = 0, SV_MEM_DEVICE = 1 };
 enum { SV_LEFT = 0, SV_RIGHT = 1 };
 /* cv::StereoSGBM mode constants (src/lib.cpp:259 uses MODE_HH4) */
-enum { SV_MODE_SGBM = 0, SV_MODE_HH = 1, SV_MODE_SGBM_3WAY = 2 /* unsupported */, SV_MODE_HH4 = 3 };
+enum { SV_MODE_SGBM = 0, SV_MODE_HH = 1, SV_MODE_SGBM_3WAY = 2, SV_MODE_HH4 = 3 };
 
 /* The setter block of src/lib.cpp:249-259, one field per cv::StereoSGBM setter.
  * Values are normalised the way OpenCV does (P1<=0 -> 2, uniquenessRatio<0 -> 10, ...). */

@@ -214,6 +214,8 @@ int svo_sgbm_compute_cn(const uint8_t* left, const uint8_t* right, int W, int H,
   if (mode == SVO_MODE_SGBM_3WAY && uniq >= 100) return -2;
   if (mode != SVO_MODE_SGBM && mode != SVO_MODE_HH && mode != SVO_MODE_HH4 && mode != SVO_MODE_SGBM_3WAY) return -2;
   /* cv2 raises for MODE_SGBM / MODE_HH when width - (minD + D) <= blockSize/2; MODE_HH4 does not */
+  /* (MODE_SGBM_3WAY has no such check in cv2 - it fails in an allocation for a negative width and returns values that
+   * are not pinned here for 0 < width - (minD + D) <= blockSize/2 - the restatement refuses those images as well) */
   if (mode != SVO_MODE_HH4 && W - (minD + D) <= bs / 2) return -2;
 
   for (int y = 0; y < H; y++) {

@@ -44,6 +44,29 @@ def test_sgbm_three_channel_golden(svgpu, oracle):
         assert e.value.code == svgpu._abi.SV_INVALID_SETTINGS
 
 
+def test_sgbm_3way_golden(svgpu, oracle):
+    """MODE_SGBM_3WAY (four stripe frames per pair, forward H+V sweep, backward H sweep, OpenCV's vectorised selection rule):
+    bit-exact against cv2's output incl. noise pairs (ties) and images smaller than the stripe overlap; batch == single; an
+    8UC3 pair against the oracle; uniquenessRatio = 100 is refused (cv2 dies with SIGFPE there)."""
+    from helpers import sgbm3way_golden_cases
+    for i, l, r, prm, want in sgbm3way_golden_cases():
+        with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
+            ctx.set_sgbm(**prm)
+            assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
+            if i % 5 == 0:
+                got = ctx.sgbm_batch(np.stack([l, r, l]), np.stack([r, l, r]))
+                assert nmismatch(got[0], want) == 0 and nmismatch(got[2], want) == 0, (i, prm)
+    rng = np.random.default_rng(3)
+    l3 = rng.integers(0, 256, (45, 150, 3), dtype=np.uint8)
+    r3 = np.roll(l3, -7, axis=1)
+    prm = dict(REF_PARAMS, numDisparities=32, blockSize=5, P1=200, P2=800, mode=2)
+    with svgpu.Context(150, 45) as ctx:
+        ctx.set_sgbm(**prm)
+        assert nmismatch(ctx.sgbm(l3, r3), oracle.sgbm(l3, r3, **prm)) == 0
+        with pytest.raises(svgpu.SvgpuError):
+            ctx.set_sgbm(**dict(prm, uniquenessRatio=100))
+
+
 def test_sgbm_too_narrow_matches_reference_error(svgpu):
     l = np.zeros((21, 40), np.uint8)
     with svgpu.Context(40, 21) as ctx:
@@ -58,7 +81,7 @@ def test_sgbm_too_narrow_matches_reference_error(svgpu):
 
 def test_invalid_settings_and_images(svgpu):
     with svgpu.Context(64, 48) as ctx:
-        for bad in (dict(numDisparities=24), dict(numDisparities=512), dict(numDisparities=32, mode=2),
+        for bad in (dict(numDisparities=24), dict(numDisparities=512), dict(numDisparities=32, mode=4), dict(numDisparities=32, mode=2, uniquenessRatio=100),
                     dict(numDisparities=32, blockSize=4), dict(numDisparities=32, P2=30000)):
             prm = dict(REF_PARAMS, mode=1)
             prm.update(bad)
