@@ -173,8 +173,13 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
     cs.H = g.Hs;
     const size_t cellsStripe = (size_t)cfg.W1 * g.Hs * cfg.D;
     const size_t planeRowBytes = (size_t)2 * cn * cfg.Wp * sizeof(uint2);
-    // rows of a stripe frame below its stripe are never produced: keep them defined
-    SV_RET(cudaMemsetAsync(sc.C, 0, (size_t)nframes * 4 * cellsStripe * 2, st));
+    // rows of a stripe frame below its stripe are never produced (only the first stripe is shorter than Hs): keep them defined
+    for (int s = 0; s < 4; s++) {
+      if (g.rows[s] >= g.Hs) continue;
+      const size_t rowBytes = (size_t)cfg.W1 * cfg.D * 2;
+      SV_RET(cudaMemset2DAsync(sc.C + s * cellsStripe + (size_t)g.rows[s] * cfg.W1 * cfg.D, 4 * cellsStripe * 2, 0,
+                               (size_t)(g.Hs - g.rows[s]) * rowBytes, nframes, st));
+    }
     for (int s = 0; s < 4; s++) {
       if (g.rows[s] <= 0) continue;
       SgbmCfg cc = cfg;
