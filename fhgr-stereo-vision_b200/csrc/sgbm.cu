@@ -37,10 +37,11 @@ __device__ __forceinline__ int pf_int(const uint8_t* r, int x, int W, int cn, in
 
 // Plane order of a row: [channel][gradient, intensity][Wp] (cn = 3: StereoSGBM sums the cost over the colour channels,
 // each with its own gradient and intensity term)
+template <int cn>
 __global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restrict__ left, size_t lstride, size_t lframe,
                                                           const uint8_t* __restrict__ right, size_t rstride, size_t rframe,
                                                           uint8_t* __restrict__ planesL, uint8_t* __restrict__ planesR,
-                                                          int W, int H, int Wp, int cn, int ftzero) {
+                                                          int W, int H, int Wp, int ftzero) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restr
   const size_t stride = side ? rstride : lstride;
   auto h16 = [](int v) { return (uint32_t)v & 0xFFFFu; };
   uint2* p = (uint2*)(side ? planesR : planesL) + ((size_t)frame * H + y) * 2 * cn * Wp + x;
+#pragma unroll
   for (int c = 0; c < cn; c++, p += 2 * Wp) {
     const uint8_t* r = img + (size_t)y * stride + c;
     const uint8_t* u = y > 0 ? r - stride : r;
@@ -163,8 +165,10 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
   if (ev) SV_RET(cudaEventRecord(ev[0], st));
   {
     dim3 g((W + 255) / 256, H, nframes * 2);
-    k_prefilter_planes<<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H,
-                                          cfg.Wp, cn, cfg.ftzero);
+    if (cn == 3)
+      k_prefilter_planes<3><<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H, cfg.Wp, cfg.ftzero);
+    else
+      k_prefilter_planes<1><<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H, cfg.Wp, cfg.ftzero);
     SV_LAUNCHED();
   }
   if (cfg.mode == SV_MODE_SGBM_3WAY) {
