@@ -75,6 +75,75 @@ __global__ void __launch_bounds__(256) k_prefilter_planes(const uint8_t* __restr
   }
 }
 
+// Single-channel fast path: four neighbouring pixels per thread, the three image rows read as aligned 32-bit words, every
+// column sum of the Sobel filter computed once (needs W % 4 == 0 and 4-byte aligned rows; otherwise the kernel above runs).
+__global__ void __launch_bounds__(256) k_prefilter_planes_x4(const uint8_t* __restrict__ left, size_t lstride, size_t lframe,
+                                                             const uint8_t* __restrict__ right, size_t rstride, size_t rframe,
+                                                             uint8_t* __restrict__ planesL, uint8_t* __restrict__ planesR,
+                                                             int W, int H, int Wp, int ftzero) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
+  if (x0 >= W) return;
+  const uint8_t* img = side ? right + frame * rframe : left + frame * lframe;
+  const size_t stride = side ? rstride : lstride;
+  const uint8_t* rows[3];
+  rows[1] = img + (size_t)y * stride;
+  rows[0] = y > 0 ? rows[1] - stride : rows[1];
+  rows[2] = y < H - 1 ? rows[1] + stride : rows[1];
+  int cs[8], ctr[8];  // column sums u + 2r + d and the centre row, columns x0-2 .. x0+5
+#pragma unroll
+  for (int k = 0; k < 8; k++) cs[k] = ctr[k] = 0;
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const uint32_t* w = (const uint32_t*)(rows[q] + x0);
+    const uint32_t w0 = x0 >= 4 ? __ldg(w - 1) : 0u, w1 = __ldg(w), w2 = x0 + 4 < W ? __ldg(w + 1) : 0u;
+    const int b[8] = {(int)((w0 >> 16) & 255), (int)(w0 >> 24), (int)(w1 & 255), (int)((w1 >> 8) & 255), (int)((w1 >> 16) & 255), (int)(w1 >> 24),
+                      (int)(w2 & 255), (int)((w2 >> 8) & 255)};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      cs[k] += q == 1 ? 2 * b[k] : b[k];
+      if (q == 1) ctr[k] = b[k];
+    }
+  }
+  int g[6], it[6];  // pre-filtered gradient and intensity of columns x0-1 .. x0+4
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const int x = x0 - 1 + j;
+    const bool border = x <= 0 || x >= W - 1;
+    g[j] = border ? ftzero : min(max(cs[j + 2] - cs[j], -ftzero), ftzero) + ftzero;
+    it[j] = border ? ftzero : ctr[j + 1];
+  }
+  auto h16 = [](int v) { return (uint32_t)v & 0xFFFFu; };
+  uint32_t og[8], oi[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int x = x0 + j;
+    const int g0 = g[j + 1], i0 = it[j + 1];
+    int glo = g0, ghi = g0, ilo = i0, ihi = i0;
+    if (x > 0) {
+      const int a = (g0 + g[j]) >> 1, c = (i0 + it[j]) >> 1;
+      glo = min(glo, a); ghi = max(ghi, a); ilo = min(ilo, c); ihi = max(ihi, c);
+    }
+    if (x < W - 1) {
+      const int a = (g0 + g[j + 2]) >> 1, c = (i0 + it[j + 2]) >> 1;
+      glo = min(glo, a); ghi = max(ghi, a); ilo = min(ilo, c); ihi = max(ihi, c);
+    }
+    if (side == 0) {
+      og[2 * j] = h16(glo) | h16(g0) << 16; og[2 * j + 1] = h16(-ghi) | h16(-g0) << 16;
+      oi[2 * j] = h16(ilo) | h16(i0) << 16; oi[2 * j + 1] = h16(-ihi) | h16(-i0) << 16;
+    } else {
+      og[2 * j] = h16(-g0) | h16(-ghi) << 16; og[2 * j + 1] = h16(g0) | h16(glo) << 16;
+      oi[2 * j] = h16(-i0) | h16(-ihi) << 16; oi[2 * j + 1] = h16(i0) | h16(ilo) << 16;
+    }
+  }
+  uint2* p = (uint2*)(side ? planesR : planesL) + ((size_t)frame * H + y) * 2 * Wp + x0;
+  ((uint4*)p)[0] = make_uint4(og[0], og[1], og[2], og[3]);
+  ((uint4*)p)[1] = make_uint4(og[4], og[5], og[6], og[7]);
+  ((uint4*)(p + Wp))[0] = make_uint4(oi[0], oi[1], oi[2], oi[3]);
+  ((uint4*)(p + Wp))[1] = make_uint4(oi[4], oi[5], oi[6], oi[7]);
+}
+
 // K5: sub-pixel disparity + left-right consistency check of one image row (A.6, second half), from the
 // per-pixel selection the second sweep left in `sel`.  disp2 is rebuilt by a scatter-min of
 // (minS, W1-1-x') keys: lowest cost wins, ties go to the largest x' — the same winner as OpenCV's
@@ -165,7 +234,11 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
   if (ev) SV_RET(cudaEventRecord(ev[0], st));
   {
     dim3 g((W + 255) / 256, H, nframes * 2);
-    if (cn == 3)
+    const bool x4 = cn == 1 && W % 4 == 0 && ((uintptr_t)left | (uintptr_t)right | lstride | rstride | lframe | rframe) % 4 == 0;
+    if (x4) {
+      dim3 g4((W / 4 + 255) / 256, H, nframes * 2);
+      k_prefilter_planes_x4<<<g4, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H, cfg.Wp, cfg.ftzero);
+    } else if (cn == 3)
       k_prefilter_planes<3><<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H, cfg.Wp, cfg.ftzero);
     else
       k_prefilter_planes<1><<<g, 256, 0, st>>>(left, lstride, lframe, right, rstride, rframe, sc.planesL, sc.planesR, W, H, cfg.Wp, cfg.ftzero);
