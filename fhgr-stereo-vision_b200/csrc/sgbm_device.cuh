@@ -67,9 +67,12 @@ __device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, int lane) {
 //   x = min3_s16(L(d-1), L(d+1), m+P2-P1);  y = min_u16(x+P1, L(d));  L' = y + C + (-m)
 // (3 instructions per packed register; no half ever borrows or carries because m <= y and y + C < 2^16).
 // ------------------------------------------------------------------------------------------------
+// sweep_path_core does the step and returns the minimum over this lane's 16 disparities (in both halves; all ones for a lane
+// without disparities); the caller reduces it over the worker's lanes — alone (sweep_path_step) or two paths at a time in
+// the two halves of one register (group_min2_u16), which halves the number of shuffles.
 template <int LPP>
-__device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& mdup, bool outside, const uint32_t (&c)[kNR],
-                                                const SweepK& k, int gl, int lastLane, bool active, int lane) {
+__device__ __forceinline__ uint32_t sweep_path_core(uint32_t (&L)[kNR], uint32_t mdup, bool outside, const uint32_t (&c)[kNR],
+                                                    const SweepK& k, int gl, int lastLane, bool active, int lane) {
   uint32_t up = kMax2, dn = kMax2;
   if (LPP > 1) {
     up = __shfl_up_sync(0xFFFFFFFFu, L[kNR - 1], 1, LPP);
@@ -95,9 +98,28 @@ __device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& md
   mn = __vminu2(mn, n[7]);
   mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
   if (!active) mn = 0xFFFFFFFFu;
-  mdup = group_min_u32<LPP>(mn, lane);
 #pragma unroll
   for (int i = 0; i < kNR; i++) L[i] = n[i];
+  return mn;
+}
+template <int LPP>
+__device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& mdup, bool outside, const uint32_t (&c)[kNR],
+                                                const SweepK& k, int gl, int lastLane, bool active, int lane) {
+  mdup = group_min_u32<LPP>(sweep_path_core<LPP>(L, mdup, outside, c, k, gl, lastLane, active, lane), lane);
+}
+// minima of two paths over the worker's lanes with one butterfly: a and b hold a lane-local minimum in both halves
+template <int LPP>
+__device__ __forceinline__ void group_min2_u16(uint32_t a, uint32_t b, int lane, uint32_t& ma, uint32_t& mb) {
+  if constexpr (LPP == 16) {  // two full-warp CREDUX per path (see group_min_u32)
+    ma = group_min_u32<LPP>(a, lane);
+    mb = group_min_u32<LPP>(b, lane);
+  } else {
+    uint32_t p = __byte_perm(a, b, 0x5410);  // low half: path a, high half: path b
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) p = __vminu2(p, __shfl_xor_sync(0xFFFFFFFFu, p, o));
+    ma = __byte_perm(p, 0, 0x1010);
+    mb = __byte_perm(p, 0, 0x3232);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -62,6 +62,9 @@ namespace {
 #ifndef SV_SWEEP_UNCOND
 #define SV_SWEEP_UNCOND 1
 #endif
+#ifndef SV_SWEEP_MIN2
+#define SV_SWEEP_MIN2 1      // 1: the minima of two paths share one shuffle butterfly, 0: one butterfly per path
+#endif
 #ifndef SV_SWEEP_FAKE
 #define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
 #endif
@@ -468,6 +471,34 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         const uint32_t omV = recM[i][0], omDL = recM[i][1];
         uint32_t mDR = recM[i][2];
         // ---- the min-plus steps (A.5); a predecessor outside the volume is expressed through the scalars
+#if SV_SWEEP_MIN2
+        // the minima of two paths share one shuffle butterfly: (H, DR) and (V, DL) — or (H, V) without diagonals.  The
+        // partner of the horizontal path is computed first, so that nothing waits for H longer than before.
+        uint32_t sum[kNR];
+        uint32_t mV = mVd1, mDL = mDLd2;
+        if (HAS_DR) {
+          const uint32_t lDR = sweep_path_core<LPP>(DRin, mDR, !on || top || x == W1 - 1, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP>(lH, lDR, lane, mH, mDR);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(Hs[q], DRin[q], kMax2);
+          const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lDL = sweep_path_core<LPP>(DLd2, mDL, !on || top || x == 0, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP>(lV, lDL, lane, mV, mDL);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(__viaddmin_u16x2(sum[q], Vd1[q], kMax2), DLd2[q], kMax2);
+        } else if (HAS_V) {
+          const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP>(lH, lV, lane, mH, mV);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(Hs[q], Vd1[q], kMax2);
+        } else {
+          sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+#pragma unroll
+          for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
+        }
+#else
         sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
         uint32_t sum[kNR];
 #pragma unroll
@@ -488,6 +519,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DRin[q], kMax2);
         }
+#endif
         // ---- new record of this slot (read by this worker in the next row)
 #pragma unroll
         for (int h = 0; h < NV; h++) {
