@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       // ================================================================== phase B: kK pixels
       const int yp = a.flip ? H - 1 - r : r;
       const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
+      // volume offsets of the chunk's first pixel in this row and of the first pixel fetched for the next row; the chunk
+      // walks them in steps of +-pixU4 (pass 2 runs on the flipped volume)
+      const int stepU4 = a.flip ? -a.pixU4 : a.pixU4;
+      const unsigned offRow0 = (unsigned)yp * a.rowU4 + (unsigned)(a.flip ? W1 - 1 - xl : xl) * (unsigned)a.pixU4;
+      const unsigned offNext0 = (unsigned)ypn * a.rowU4 + (unsigned)(a.flip ? W1 - xl : xl - 1) * (unsigned)a.pixU4;
+      uint2* selRow = SECOND ? a.sel + ((size_t)frame * H + (act ? yp : 0)) * W1 : nullptr;  // selection output row of this step
       const bool actn = (r + 1) >= y0 && (r + 1) <= y1;
       const bool top = r == 0;
       // export target of this chunk: the ring of the right neighbour, or (no neighbour / inactive row / neighbour in
@@ -439,10 +445,9 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         {
           const int xn = x - 1;
           const bool ld = actn && (unsigned)xn < (unsigned)W1;
-          const int xpn = a.flip ? W1 - 1 - xn : xn;
 #if SV_SWEEP_UNCOND
           // always load (from a safe address when there is nothing to fetch) so that the data lands in cb/sb directly
-          const unsigned off = ld ? (unsigned)ypn * a.rowU4 + (unsigned)xpn * (unsigned)a.pixU4 : 0u;
+          const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
 #pragma unroll
           for (int h = 0; h < NV; h++) {
             cb[i][h] = __ldcs(Cf + off + h);
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           }
 #else
           if (ld) {
-            const unsigned off = (unsigned)ypn * a.rowU4 + (unsigned)xpn * (unsigned)a.pixU4;
+            const unsigned off = offNext0 + (unsigned)(i * stepU4);
 #pragma unroll
             for (int h = 0; h < NV; h++) {
               cb[i][h] = __ldcs(Cf + off + h);
@@ -549,14 +554,14 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], sin[q], kMax2);
           uint2 o;
           sweep_wta<LPP, WAY3>(sum, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
-          const unsigned off = (unsigned)yp * a.rowU4 + (unsigned)xp * (unsigned)a.pixU4;
-          if (on && gl == 0) a.sel[((size_t)frame * H + yp) * W1 + xp] = o;
+          const unsigned off = offRow0 + (unsigned)(i * stepU4);
+          if (on && gl == 0) selRow[xp] = o;
           if (a.debugS && on && active) {
 #pragma unroll
             for (int h = 0; h < NV; h++) Sf[off + h] = make_uint4(sum[4 * h], sum[4 * h + 1], sum[4 * h + 2], sum[4 * h + 3]);
           }
         } else if (on && active) {
-          const unsigned off = (unsigned)yp * a.rowU4 + (unsigned)xp * (unsigned)a.pixU4;
+          const unsigned off = offRow0 + (unsigned)(i * stepU4);
 #pragma unroll
           for (int h = 0; h < NV; h++) __stcs(Sf + off + h, make_uint4(sum[4 * h], sum[4 * h + 1], sum[4 * h + 2], sum[4 * h + 3]));
         }
