@@ -196,7 +196,8 @@ __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int
   return true;
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
+// FULL: every lane of a worker holds disparities (D is LPP x 16), so the "lane without disparities" cases fold away
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false, bool FULL = false>
 __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_sweep(const SweepArgs a) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
 #endif
   const int j = lane / LPP, gl = lane % LPP;
   const int W1 = a.W1, H = a.H;
-  const bool active = gl < a.nAct;           // lane holds disparities
+  const bool active = FULL ? true : gl < a.nAct;  // lane holds disparities
   const int lastLane = a.nAct - 1;
   SweepK kc;
   kc.p1dup = a.p1dup; kc.p2mp1dup = a.p2mp1dup; kc.negp1dup = a.negp1dup;
@@ -643,14 +644,21 @@ int groups_of(const SgbmCfg& cfg, bool second, bool low) {
   return (smax_of(cfg) + 1 + spc - 1) / spc;
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
-cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3, bool FULL>
+cudaError_t launch_full(const SweepArgs& a, int grid, cudaStream_t st) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
-  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3>;
+  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3, FULL>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return e;
   k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
+cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
+  // the specialisation without idle lanes is built for the throughput kernels of the common modes only
+  if (a.nAct == LPP && MAXNW == kMaxNW && !WAY3) return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true>(a, grid, st);
+  return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, false>(a, grid, st);
 }
 
 template <int LPP, int PATHS, bool SECOND, bool WAY3 = false>
