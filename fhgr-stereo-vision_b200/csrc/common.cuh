@@ -93,7 +93,7 @@ struct CostView {
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& view, int nframes, int cn, cudaStream_t st);
 // sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
-                                 LaunchStats* stats);
+                                 LaunchStats* stats, int cn = 1);
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
 

@@ -269,7 +269,7 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
     if (ev) SV_RET(cudaEventRecord(ev[1], st));
     SgbmScratch ss = sc;
     ss.frameCells = cellsStripe;
-    SV_RET(sgbm_aggregate_sweep(cs, ss, nframes * 4, 0, st, stats));
+    SV_RET(sgbm_aggregate_sweep(cs, ss, nframes * 4, 0, st, stats, cn));
     if (ev) SV_RET(cudaEventRecord(ev[2], st));
     int16_t* dispStripes = sc.dispRaw;
     int16_t* dispFull = sc.dispRaw + (size_t)nframes * 4 * g.Hs * W;
@@ -292,7 +292,7 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
   }
   if (stats) stats->launches++;
   if (ev) SV_RET(cudaEventRecord(ev[1], st));
-  SV_RET(sgbm_aggregate_sweep(cfg, sc, nframes, debugS, st, stats));
+  SV_RET(sgbm_aggregate_sweep(cfg, sc, nframes, debugS, st, stats, cn));
   if (ev) SV_RET(cudaEventRecord(ev[2], st));
   {
     dim3 g(H, nframes);

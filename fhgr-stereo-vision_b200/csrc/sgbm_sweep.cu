@@ -123,6 +123,7 @@ struct SweepArgs {
   unsigned rowU4;              // uint4 per volume row = W1*D/8
   int pixU4;                   // uint4 per pixel = D/8
   uint32_t p1dup, p2mp1dup, negp1dup;
+  int smallSums;               // 4 x (largest block cost + P2) <= 32767: a pass may add its path costs without saturation
   int uniqF;                   // 100 - uniquenessRatio
   uint32_t uniqMagic;          // ceil(2^32 / uniqF) for uniqF >= 2
 };
@@ -197,7 +198,9 @@ __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int
 }
 
 // FULL: every lane of a worker holds disparities (D is LPP x 16), so the "lane without disparities" cases fold away
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false, bool FULL = false>
+// SMALL: four path costs of a pixel sum to less than 2^15 (4 x (largest block cost + P2) <= 32767, checked on the host), so a
+//        pass can add them with plain (three-input) adds and only the final S of pass 2 needs the saturation of A.5
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false, bool FULL = false, bool SMALL = false>
 __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_sweep(const SweepArgs a) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
@@ -487,18 +490,19 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP>(lH, lDR, lane, mH, mDR);
 #pragma unroll
-          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(Hs[q], DRin[q], kMax2);
+          for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + DRin[q] : __viaddmin_u16x2(Hs[q], DRin[q], kMax2);
           const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
           const uint32_t lDL = sweep_path_core<LPP>(DLd2, mDL, !on || top || x == 0, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP>(lV, lDL, lane, mV, mDL);
 #pragma unroll
-          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(__viaddmin_u16x2(sum[q], Vd1[q], kMax2), DLd2[q], kMax2);
+          for (int q = 0; q < kNR; q++)
+            sum[q] = SMALL ? sum[q] + Vd1[q] + DLd2[q] : __viaddmin_u16x2(__viaddmin_u16x2(sum[q], Vd1[q], kMax2), DLd2[q], kMax2);
         } else if (HAS_V) {
           const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
           const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP>(lH, lV, lane, mH, mV);
 #pragma unroll
-          for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(Hs[q], Vd1[q], kMax2);
+          for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + Vd1[q] : __viaddmin_u16x2(Hs[q], Vd1[q], kMax2);
         } else {
           sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
 #pragma unroll
@@ -644,10 +648,10 @@ int groups_of(const SgbmCfg& cfg, bool second, bool low) {
   return (smax_of(cfg) + 1 + spc - 1) / spc;
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3, bool FULL>
+template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3, bool FULL, bool SMALL = false>
 cudaError_t launch_full(const SweepArgs& a, int grid, cudaStream_t st) {
   using G = SweepGeom<LPP, SECOND, MAXNW>;
-  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3, FULL>;
+  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3, FULL, SMALL>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return e;
   k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
@@ -657,7 +661,10 @@ cudaError_t launch_full(const SweepArgs& a, int grid, cudaStream_t st) {
 template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
 cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
   // the specialisation without idle lanes is built for the throughput kernels of the common modes only
-  if (a.nAct == LPP && MAXNW == kMaxNW && !WAY3) return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true>(a, grid, st);
+  if (a.nAct == LPP && MAXNW == kMaxNW && !WAY3) {
+    if (a.smallSums && PATHS == 15) return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true, true>(a, grid, st);
+    return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true>(a, grid, st);
+  }
   return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, false>(a, grid, st);
 }
 
@@ -692,7 +699,7 @@ size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
 
 // Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
-                                 LaunchStats* stats) {
+                                 LaunchStats* stats, int cn) {
   int dev = 0, numSM = 0;
   cudaError_t e0 = cudaGetDevice(&dev);
   if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);
@@ -704,6 +711,8 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.gprog = (int*)sc.flags + 64;
   a.status = sc.status;
   a.W1 = cfg.W1; a.H = cfg.H; a.D = cfg.D; a.nAct = cfg.D / kDPL;
+  // largest block cost of single-channel input: blockSize^2 x (2 ftzero + 63); every path cost is <= that + P2 (A.5)
+  a.smallSums = cn <= 1 && 4ll * ((2 * cfg.r + 1) * (2 * cfg.r + 1) * (2 * cfg.ftzero + 63) + cfg.P2) <= 32767;
   a.nframes = nframes; a.smax = smax_of(cfg); a.debugS = debugS;
   a.frameU4 = (unsigned)(sc.frameCells / 8);
   a.pixU4 = cfg.D / 8;
