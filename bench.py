@@ -264,16 +264,17 @@ def main():
                     "achieved": launch_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": launch_bytes / launch_s / 1e9 / hbm_peak, "traffic": 1.03e9 * B, "peak_source": which,
                     "algorithmic_bytes_per_launch": launch_bytes, "launch_ms": launch_s * 1e3, "stage_ms_per_step": stage,
-                    "note": "the sweeps are bound by the packed-integer ALU pipe (ncu: ~50 % of the pipe over the launch), not by HBM; "
+                    "note": "the sweeps are bound by the packed-integer ALU pipe (ncu: ~60 % of the pipe over the launch, profiles/r01_v7_summary.md), not by HBM; "
                             "HBM is reported because it is the only peak with a driver-measured denominator",
                     "cost_kernel": {"bytes_per_cell": 2, "achieved": 2.0 * cells * B / (stage["cost"] / 1e3) / 1e9,
                                     "frac": 2.0 * cells * B / (stage["cost"] / 1e3) / 1e9 / hbm_peak},
-                    # integer roofline of the whole chain: SURVEY.md §8d counts 102 16-bit lane-operations per volume cell for the
-                    # 8-path mode; peak = packed-integer (ALU) pipe as measured by tools/ubench_int16x2.cu on B200:
-                    # 2.0 warp-instructions / clk / SM x 32 lanes x 2 halves x 148 SMs x 1.965 GHz
-                    "int_pipe": {"ops_per_cell": 102, "achieved_tops": 102.0 * cells * pairs / (ms_max / 1e3) / 1e12 / world,
+                    # integer roofline of the whole chain: 85 16-bit lane-operations per volume cell on the packed-integer (ALU)
+                    # pipe, as executed by the three hot kernels in the ncu capture of variant 8 (profiles/r01_v8_ncu_raw.csv;
+                    # SURVEY.md §8d's algorithmic count for the 8-path mode is 102); peak = that pipe as measured by
+                    # tools/ubench_int16x2.cu on B200: 2.0 warp-instructions / clk / SM x 32 lanes x 2 halves x 148 SMs x 1.965 GHz
+                    "int_pipe": {"ops_per_cell": 85, "achieved_tops": 85.0 * cells * pairs / (ms_max / 1e3) / 1e12 / world,
                                  "peak_tops": 2.0 * 32 * 2 * 148 * 1.965e9 / 1e12,
-                                 "frac": 102.0 * cells * pairs / (ms_max / 1e3) / world / (2.0 * 32 * 2 * 148 * 1.965e9)},
+                                 "frac": 85.0 * cells * pairs / (ms_max / 1e3) / world / (2.0 * 32 * 2 * 148 * 1.965e9)},
                     "chain": {"bytes_per_cell": 10, "achieved": 10.0 * cells * B / (stage["total"] / 1e3) / 1e9,
                               "frac": 10.0 * cells * B / (stage["total"] / 1e3) / 1e9 / hbm_peak}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
