@@ -31,12 +31,10 @@ struct svgpu_ctx {
   bool debugS = false;  // test hook: the second sweep also stores the final S volume
 
   int maxBatch = 1;
-  // scratch for the SGBM core, sized for (cfg, allocBatch)
+  // scratch for the SGBM core; every buffer keyed on its byte size (ensure_scratch)
   SgbmScratch sc{};
-  int allocBatch = 0;
-  size_t allocCells = 0;
-  int allocWp = 0;
-  int allocCn = 0;   // colour channels the operand planes are sized for
+  static constexpr int kScratchBufs = 9;
+  size_t allocBytes[kScratchBufs] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // planesL, planesR, C, S, sel, dispRaw, status, flags, edges
   // device staging of caller images for SV_MEM_HOST calls and intermediates of the fused chain
   std::vector<void*> pool;  // everything cudaMalloc'ed lazily through dev_buf()
   struct Buf { void* p = nullptr; size_t n = 0; };
@@ -82,13 +80,16 @@ void free_scratch(svgpu_ctx* c) {
   cudaFree(c->sc.planesL); cudaFree(c->sc.planesR); cudaFree(c->sc.C); cudaFree(c->sc.S); cudaFree(c->sc.sel);
   cudaFree(c->sc.dispRaw); cudaFree(c->sc.status); cudaFree(c->sc.flags); cudaFree(c->sc.edges);
   c->sc = SgbmScratch{};
-  c->allocBatch = 0; c->allocCells = 0; c->allocWp = 0; c->allocCn = 0;
+  for (size_t& b : c->allocBytes) b = 0;
 }
 
 // the sweep kernels raise sc.status when a hand-over timed out (which would mean a scheduling bug or a device
 // fault); surfaced at every point where the host waits for the stream anyway
 int check_status(svgpu_ctx* c) {
-  if (!c->sc.status) return SV_OK;
+  if (!c->sc.status) {  // no SGBM call yet: still wait for the stream (callers rely on their copies being done)
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    return e == cudaSuccess ? SV_OK : cuda_fail(c, e, "stream synchronize");
+  }
   int h = 0;
   cudaError_t e = cudaMemcpyAsync(&h, c->sc.status, sizeof(int), cudaMemcpyDeviceToHost, c->st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
@@ -100,6 +101,9 @@ int check_status(svgpu_ctx* c) {
   return SV_OK;
 }
 
+// Scratch of the SGBM core for `batch` pairs of the current configuration.  Every buffer is keyed on its own byte size
+// (they depend on W1, D, the mode, the block radius and the strip-group count individually, not only on the cell count):
+// a reconfiguration that needs more of any buffer reallocates, one that needs less reuses what is there.
 int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   const SgbmCfg& g = c->cfg;
   // MODE_SGBM_3WAY works on four stripe frames per pair (common.cuh: StripeGeom): volumes, selection and the sweep's
@@ -110,29 +114,32 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   if (way3) gs.H = vrows / 4;
   const int sweepFrames = way3 ? batch * 4 : batch;
   const size_t cells = g.W1 > 0 ? (size_t)g.W1 * vrows * g.D : 0;
-  if (c->allocBatch >= batch && c->allocCells == cells && c->allocWp == g.Wp && c->allocCn >= cn && c->sc.dispRaw) return SV_OK;
-  batch = std::max(batch, c->allocBatch);
-  cn = std::max(cn, c->allocCn);
-  free_scratch(c);
-  const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2);
   const size_t w1 = g.W1 > 0 ? g.W1 : 0;
+  const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2);
+  const size_t need[svgpu_ctx::kScratchBufs] = {
+      planeBytes, planeBytes, (size_t)batch * cells * 2, (size_t)batch * cells * 2, (size_t)batch * vrows * w1 * 8,
+      (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2, 256, sgbm_flags_bytes(gs, sweepFrames), sgbm_edges_bytes(gs, sweepFrames)};
+  bool fits = c->sc.dispRaw != nullptr;
+  for (int i = 0; i < svgpu_ctx::kScratchBufs; i++) fits = fits && c->allocBytes[i] >= need[i];
+  if (fits) {
+    c->sc.frameCells = cells;
+    return SV_OK;
+  }
+  // work that still uses the old buffers must be done before they go away
+  cudaStreamSynchronize(c->st);
+  size_t want[svgpu_ctx::kScratchBufs];
+  for (int i = 0; i < svgpu_ctx::kScratchBufs; i++) want[i] = std::max<size_t>(std::max(need[i], c->allocBytes[i]), 256);
+  free_scratch(c);
+  void** ptrs[svgpu_ctx::kScratchBufs] = {(void**)&c->sc.planesL, (void**)&c->sc.planesR, (void**)&c->sc.C, (void**)&c->sc.S, (void**)&c->sc.sel,
+                                          (void**)&c->sc.dispRaw, (void**)&c->sc.status, (void**)&c->sc.flags, (void**)&c->sc.edges};
   cudaError_t e = cudaSuccess;
-  auto A = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 256)); };
-  A((void**)&c->sc.planesL, planeBytes);
-  A((void**)&c->sc.planesR, planeBytes);
-  A((void**)&c->sc.C, (size_t)batch * cells * 2);
-  A((void**)&c->sc.S, (size_t)batch * cells * 2);
-  A((void**)&c->sc.sel, (size_t)batch * vrows * w1 * 8);
-  A((void**)&c->sc.dispRaw, (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2);
-  A((void**)&c->sc.status, 256);
-  A((void**)&c->sc.flags, sgbm_flags_bytes(gs, sweepFrames));
-  A((void**)&c->sc.edges, sgbm_edges_bytes(gs, sweepFrames));
+  for (int i = 0; i < svgpu_ctx::kScratchBufs && e == cudaSuccess; i++) e = cudaMalloc(ptrs[i], want[i]);
   if (e != cudaSuccess) { free_scratch(c); return cuda_fail(c, e, "cudaMalloc(sgbm scratch)"); }
-  cudaMemsetAsync(c->sc.status, 0, 256, c->st);
-  cudaMemsetAsync(c->sc.flags, 0, sgbm_flags_bytes(gs, sweepFrames), c->st);
-  cudaMemsetAsync(c->sc.edges, 0, sgbm_edges_bytes(gs, sweepFrames), c->st);  // launch tags start at 1
+  for (int i = 0; i < svgpu_ctx::kScratchBufs; i++) c->allocBytes[i] = want[i];
+  cudaMemsetAsync(c->sc.status, 0, want[6], c->st);
+  cudaMemsetAsync(c->sc.flags, 0, want[7], c->st);
+  cudaMemsetAsync(c->sc.edges, 0, want[8], c->st);
   c->sc.frameCells = cells;
-  c->allocBatch = batch; c->allocCells = cells; c->allocWp = g.Wp; c->allocCn = cn;
   return SV_OK;
 }
 
@@ -396,6 +403,8 @@ SVGPU_API int svgpu_set_bm(svgpu_ctx* c, const svgpu_bm_params* p) {
   if (p->minDisparity < -1024 || p->minDisparity + p->numDisparities > 1024) return fail(c, SV_INVALID_SETTINGS, "bm disparity range must lie within [-1024, 1024]");
   if (p->disp12MaxDiff >= 0) return fail(c, SV_INVALID_SETTINGS, "bm disp12MaxDiff >= 0 is not supported");
   if ((long long)p->blockSize * p->blockSize * 2 * p->preFilterCap > 65535) return fail(c, SV_INVALID_SETTINGS, "bm blockSize^2*2*cap exceeds the 16-bit SAD range");
+  if (bm_smem_bytes(p->numDisparities, p->blockSize) > 227 * 1024)
+    return fail(c, SV_INVALID_SETTINGS, "bm: (blockSize + 1) x (32 + blockSize) x numDisparities bytes of row ring exceed the 227 KB of shared memory per SM; reduce blockSize or numDisparities");
   BmCfg b{};
   b.W = c->W; b.H = c->H; b.D = p->numDisparities; b.minD = p->minDisparity; b.bs = p->blockSize; b.cap = p->preFilterCap;
   b.tex = p->textureThreshold; b.uniq = p->uniquenessRatio; b.d12 = p->disp12MaxDiff; b.filtered = (b.minD - 1) * 16;

@@ -202,6 +202,8 @@ __global__ void k_fill_rows(int16_t* p, size_t stride, int W, int H, int v) {
   if (x < W) *(int16_t*)((uint8_t*)p + (size_t)y * stride + (size_t)x * 2) = (int16_t)v;
 }
 
+size_t bm_smem_bytes(int D, int blockSize) { return bm_smem_layout(D, blockSize / 2).total; }
+
 cudaError_t bm_forward(const BmCfg& cfg, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
                        uint8_t* pfL, uint8_t* pfR, int16_t* disp, size_t dstride, cudaStream_t st, int* nlaunch) {
   const int W = cfg.W, H = cfg.H, r = cfg.bs / 2;

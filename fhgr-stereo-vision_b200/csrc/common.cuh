@@ -126,6 +126,7 @@ cudaError_t launch_resize(const uint8_t* src, int sw, int sh, size_t sstride, in
                           size_t dstride, cudaStream_t st);
 
 // bm.cu
+size_t bm_smem_bytes(int D, int blockSize);  // dynamic shared memory k_bm_sad needs for this configuration
 cudaError_t bm_forward(const BmCfg& cfg, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
                        uint8_t* pfL, uint8_t* pfR, int16_t* disp, size_t dstride, cudaStream_t st, int* nlaunch);
 

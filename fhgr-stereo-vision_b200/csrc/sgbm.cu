@@ -221,6 +221,11 @@ __global__ void __launch_bounds__(256) k_gather_stripes(const int16_t* __restric
 #define SV_RET(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
 #define SV_LAUNCHED() do { if (stats) stats->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
+// k_select_lr keeps one row of keys + disparities (6 B per column) in dynamic shared memory: opt in beyond 48 KB (W > 8192)
+static cudaError_t select_lr_smem(size_t bytes) {
+  return bytes > 48 * 1024 ? cudaFuncSetAttribute(k_select_lr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
+
 cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, const uint8_t* left, size_t lstride,
                          size_t lframe, const uint8_t* right, size_t rstride, size_t rframe, int16_t* disp,
                          size_t dstride, size_t dframe, cudaStream_t st, LaunchStats* stats, cudaEvent_t* ev, int debugS, int cn) {
@@ -275,6 +280,7 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
     int16_t* dispFull = sc.dispRaw + (size_t)nframes * 4 * g.Hs * W;
     {
       dim3 gs(g.Hs, nframes * 4);
+      SV_RET(select_lr_smem((size_t)W * 6));
       k_select_lr<<<gs, 256, (size_t)W * 6, st>>>(sc.sel, dispStripes, cs);
       SV_LAUNCHED();
       dim3 gg((W + 255) / 256, H, nframes);
@@ -296,6 +302,7 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
   if (ev) SV_RET(cudaEventRecord(ev[2], st));
   {
     dim3 g(H, nframes);
+    SV_RET(select_lr_smem((size_t)W * 6));
     k_select_lr<<<g, 256, (size_t)W * 6, st>>>(sc.sel, sc.dispRaw, cfg);
     SV_LAUNCHED();
     SV_RET(launch_median3(sc.dispRaw, (size_t)W * 2, disp, dstride, W, H, nframes, (size_t)W * H * 2, dframe, st));

@@ -20,11 +20,34 @@ __host__ __device__ __forceinline__ uint32_t dup16(uint32_t v) { return v | (v <
 // position of disparity d inside its pixel's D costs in volume memory (uint16 index)
 __host__ __device__ __forceinline__ int vol_index(int d) { return (d & ~15) | ((d & 7) << 1) | ((d >> 3) & 1); }
 
+// compile-time tuning knobs of the path step (tools/build_variants.sh builds alternatives for A/B runs on the GPU)
+#ifndef SV_SWEEP_EDGEMAD
+#define SV_SWEEP_EDGEMAD 0   // 1: the MAX_COST neighbours of a worker's first / last lane through a multiply-add (FMA pipe) instead of a select (ALU pipe)
+#endif
+#ifndef SV_SWEEP_FMAADD
+#define SV_SWEEP_FMAADD 0    // n: the first n paths of a pixel form y + C - m with two multiply-adds (FMA pipe) instead of one three-input add (ALU pipe)
+#endif
+#ifndef SV_SWEEP_MINPAIR
+#define SV_SWEEP_MINPAIR 0   // 1: paired path minima fold the two halves of the lane minimum while packing (2 instructions fewer per pair)
+#endif
+
 struct SweepK {
   uint32_t p1dup;     // P1 | P1<<16
   uint32_t p2mp1dup;  // (P2-P1) twice
   uint32_t negp1dup;  // (-P1 mod 2^16) twice
+  // lane constants: the value from the neighbouring lane is v * keep + add (keep = 1, add = 0 inside the worker; keep = 0, add = two
+  // MAX_COST for the lane without that neighbour), and a register holding 1 that the compiler cannot see through
+  uint32_t keepUp, addUp, keepDn, addDn, one;
 };
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  asm volatile("mov.b32 %0, %0;" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
 // min / sum over the LPP lanes of a worker; every lane of the warp must call
 template <int LPP>
@@ -70,15 +93,22 @@ __device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, int lane) {
 // sweep_path_core does the step and returns the minimum over this lane's 16 disparities (in both halves; all ones for a lane
 // without disparities); the caller reduces it over the worker's lanes — alone (sweep_path_step) or two paths at a time in
 // the two halves of one register (group_min2_u16), which halves the number of shuffles.
-template <int LPP>
+// FMA2: form the new path cost with two multiply-adds; HALVES: return the lane minimum per half (low: d0..d0+7, high: d0+8..d0+15)
+// instead of the minimum over all 16 in both halves
+template <int LPP, bool FMA2 = false, bool HALVES = false>
 __device__ __forceinline__ uint32_t sweep_path_core(uint32_t (&L)[kNR], uint32_t mdup, bool outside, const uint32_t (&c)[kNR],
                                                     const SweepK& k, int gl, int lastLane, bool active, int lane) {
   uint32_t up = kMax2, dn = kMax2;
   if (LPP > 1) {
     up = __shfl_up_sync(0xFFFFFFFFu, L[kNR - 1], 1, LPP);
     dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPP);
+#if SV_SWEEP_EDGEMAD
+    up = mad_u32(up, k.keepUp, k.addUp);
+    dn = mad_u32(dn, k.keepDn, k.addDn);
+#else
     if (gl == 0) up = kMax2;         // L(q,-1) = MAX_COST
     if (gl == lastLane) dn = kMax2;  // L(q,D)  = MAX_COST
+#endif
   }
   const uint32_t capm = outside ? k.negp1dup : mdup + k.p2mp1dup;
   const uint32_t negm = outside ? 0u : 0u - mdup;
@@ -90,13 +120,14 @@ __device__ __forceinline__ uint32_t sweep_path_core(uint32_t (&L)[kNR], uint32_t
     const uint32_t lm = i ? L[i - 1] : lm0, lp = (i < kNR - 1) ? L[i + 1] : lpN;
     const uint32_t x = __vimin3_s16x2(lm, lp, capm);
     const uint32_t y = __viaddmin_u16x2(x, k.p1dup, L[i]);
-    n[i] = y + c[i] + negm;
+    if constexpr (FMA2) n[i] = mad_u32(mad_u32(y, k.one, c[i]), k.one, negm);
+    else n[i] = y + c[i] + negm;
   }
   uint32_t mn = __vimin3_u16x2(n[0], n[1], n[2]);
   mn = __vimin3_u16x2(mn, n[3], n[4]);
   mn = __vimin3_u16x2(mn, n[5], n[6]);
   mn = __vminu2(mn, n[7]);
-  mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
+  if constexpr (!HALVES) mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
   if (!active) mn = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < kNR; i++) L[i] = n[i];
@@ -107,14 +138,17 @@ __device__ __forceinline__ void sweep_path_step(uint32_t (&L)[kNR], uint32_t& md
                                                 const SweepK& k, int gl, int lastLane, bool active, int lane) {
   mdup = group_min_u32<LPP>(sweep_path_core<LPP>(L, mdup, outside, c, k, gl, lastLane, active, lane), lane);
 }
-// minima of two paths over the worker's lanes with one butterfly: a and b hold a lane-local minimum in both halves
-template <int LPP>
+// minima of two paths over the worker's lanes with one butterfly: a and b hold a lane-local minimum in both halves (HALVES: one
+// minimum per half, folded here while the two paths are packed into one register)
+template <int LPP, bool HALVES = false>
 __device__ __forceinline__ void group_min2_u16(uint32_t a, uint32_t b, int lane, uint32_t& ma, uint32_t& mb) {
   if constexpr (LPP == 16) {  // two full-warp CREDUX per path (see group_min_u32)
+    if constexpr (HALVES) { a = __vminu2(a, __byte_perm(a, a, 0x1032)); b = __vminu2(b, __byte_perm(b, b, 0x1032)); }
     ma = group_min_u32<LPP>(a, lane);
     mb = group_min_u32<LPP>(b, lane);
   } else {
     uint32_t p = __byte_perm(a, b, 0x5410);  // low half: path a, high half: path b
+    if constexpr (HALVES) p = __vminu2(p, __byte_perm(a, b, 0x7632));
 #pragma unroll
     for (int o = LPP / 2; o > 0; o >>= 1) p = __vminu2(p, __shfl_xor_sync(0xFFFFFFFFu, p, o));
     ma = __byte_perm(p, 0, 0x1010);

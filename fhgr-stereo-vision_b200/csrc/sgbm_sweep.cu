@@ -32,6 +32,7 @@
 // a packed register are simply the previous / next register of the lane (sgbm_device.cuh).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sgbm_device.cuh"
@@ -64,6 +65,9 @@ namespace {
 #endif
 #ifndef SV_SWEEP_MIN2
 #define SV_SWEEP_MIN2 1      // 1: the minima of two paths share one shuffle butterfly, 0: one butterfly per path
+#endif
+#ifndef SV_SWEEP_INTERIOR
+#define SV_SWEEP_INTERIOR 1  // 1: separate copy of the chunk code for warps whose pixels all lie strictly inside the volume
 #endif
 #ifndef SV_SWEEP_FAKE
 #define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
@@ -126,6 +130,7 @@ struct SweepArgs {
   int smallSums;               // 4 x (largest block cost + P2) <= 32767: a pass may add its path costs without saturation
   int uniqF;                   // 100 - uniquenessRatio
   uint32_t uniqMagic;          // ceil(2^32 / uniqF) for uniqF >= 2
+  uint32_t one;                // 1, as a value the compiler cannot fold (multiply-adds that must stay on the FMA pipe)
 };
 
 // Hand-over counters between the warps of a CTA live in shared memory and are accessed with plain volatile
@@ -151,7 +156,9 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// orders the generic-proxy acquire of a publication before the async-proxy (TMA) read of the published entries
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // bulk (TMA) copy global -> shared whose completion is signalled on an mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -228,6 +235,9 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
   const int lastLane = a.nAct - 1;
   SweepK kc;
   kc.p1dup = a.p1dup; kc.p2mp1dup = a.p2mp1dup; kc.negp1dup = a.negp1dup;
+  kc.keepUp = opaque_u32(gl == 0 ? 0u : 1u); kc.addUp = opaque_u32(gl == 0 ? kMax2 : 0u);
+  kc.keepDn = opaque_u32(gl == lastLane ? 0u : 1u); kc.addDn = opaque_u32(gl == lastLane ? kMax2 : 0u);
+  kc.one = a.one;
 
   // shared memory starts out as valid (zero) path costs: stale entries are read under an override only
   for (int i = threadIdx.x; i < NW * G::WARP_U4; i += blockDim.x) smem[i] = make_uint4(0, 0, 0, 0);
@@ -335,7 +345,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           auto blockEnd = [&](int from) { return min((from / kPub) * kPub + kPub, y1p + 1); };
           auto issue = [&](int from, int to) {
             __syncwarp();
-            if (lane == 0) bulk_load(ring0 + (from & (kRingX - 1)) * ENT, gin + (size_t)from * ENT, (uint32_t)(to - from) * (ENT * 16), sBar);
+            if (lane == 0) {
+              fence_proxy_async_global();
+              bulk_load(ring0 + (from & (kRingX - 1)) * ENT, gin + (size_t)from * ENT, (uint32_t)(to - from) * (ENT * 16), sBar);
+            }
           };
           auto finish = [&]() {  // wait for the block in flight
             for (int n = 0; !mbar_try_wait(sBar, barPhase);)
@@ -417,6 +430,11 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       const long long pfB0 = clock64();
 #endif
       // ================================================================== phase B: kK pixels
+      // INTERIOR: every worker of the warp is on a row that is neither the first nor the last of its strip and all its pixels
+      // (and the ones fetched for the next row) lie strictly inside the volume: no predecessor is outside, nothing is
+      // predicated.  The test is warp-uniform arithmetic on T, so the warp takes one of two copies of the chunk code.
+      auto phaseB = [&](auto interiorTag) {
+      constexpr bool IN = decltype(interiorTag)::value;
       const int yp = a.flip ? H - 1 - r : r;
       const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
       // volume offsets of the chunk's first pixel in this row and of the first pixel fetched for the next row; the chunk
@@ -424,20 +442,21 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       const int stepU4 = a.flip ? -a.pixU4 : a.pixU4;
       const unsigned offRow0 = (unsigned)yp * a.rowU4 + (unsigned)(a.flip ? W1 - 1 - xl : xl) * (unsigned)a.pixU4;
       const unsigned offNext0 = (unsigned)ypn * a.rowU4 + (unsigned)(a.flip ? W1 - xl : xl - 1) * (unsigned)a.pixU4;
-      uint2* selRow = SECOND ? a.sel + ((size_t)frame * H + (act ? yp : 0)) * W1 : nullptr;  // selection output row of this step
-      const bool actn = (r + 1) >= y0 && (r + 1) <= y1;
-      const bool top = r == 0;
+      uint2* selRow = SECOND ? a.sel + ((size_t)frame * H + ((IN || act) ? yp : 0)) * W1 : nullptr;  // selection output row of this step
+      const bool actn = IN || ((r + 1) >= y0 && (r + 1) <= y1);
+      const bool top = !IN && r == 0;
       // export target of this chunk: the ring of the right neighbour, or (no neighbour / inactive row / neighbour in
       // another CTA) a private entry that the last warp copies to global memory after the chunk
-      const bool toRing = (j < RW - 1) || (hasRight && act && !rightGlobal);
-      const bool expGlobal = (j == RW - 1) && rightGlobal && act;
+      const bool toRing = (j < RW - 1) || (hasRight && (IN || act) && !rightGlobal);
+      const bool expGlobal = (j == RW - 1) && rightGlobal && (IN || act);
       uint4* eOut = (toRing ? outRing + (r & outMask) * ENT : wbase + G::OFF_XOUT) + gl;
       uint32_t mDLprev = 0;
       uint4 eMins = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int i = 0; i < kK; i++) {
         const int x = xl + i;
-        const bool on = act && (unsigned)x < (unsigned)W1;
+        const bool on = IN || (act && (unsigned)x < (unsigned)W1);
+        const bool xFirst = !IN && x == 0, xLast = !IN && x == W1 - 1;
         const int xp = a.flip ? W1 - 1 - x : x;
         // ---- operands of this pixel were loaded one chunk ago; fetch those of the pixel below-left now
         uint32_t c[kNR], sin[kNR];
@@ -448,7 +467,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         }
         {
           const int xn = x - 1;
-          const bool ld = actn && (unsigned)xn < (unsigned)W1;
+          const bool ld = IN || (actn && (unsigned)xn < (unsigned)W1);
 #if SV_SWEEP_UNCOND
           // always load (from a safe address when there is nothing to fetch) so that the data lands in cb/sb directly
           const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
@@ -486,30 +505,32 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         uint32_t sum[kNR];
         uint32_t mV = mVd1, mDL = mDLd2;
         if (HAS_DR) {
-          const uint32_t lDR = sweep_path_core<LPP>(DRin, mDR, !on || top || x == W1 - 1, c, kc, gl, lastLane, active, lane);
-          const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
-          group_min2_u16<LPP>(lH, lDR, lane, mH, mDR);
+          constexpr bool HV = SV_SWEEP_MINPAIR != 0;
+          const uint32_t lDR = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(DRin, mDR, !on || top || xLast, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP, HV>(lH, lDR, lane, mH, mDR);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + DRin[q] : __viaddmin_u16x2(Hs[q], DRin[q], kMax2);
-          const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
-          const uint32_t lDL = sweep_path_core<LPP>(DLd2, mDL, !on || top || x == 0, c, kc, gl, lastLane, active, lane);
-          group_min2_u16<LPP>(lV, lDL, lane, mV, mDL);
+          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 1), HV>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lDL = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 2), HV>(DLd2, mDL, !on || top || xFirst, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP, HV>(lV, lDL, lane, mV, mDL);
 #pragma unroll
           for (int q = 0; q < kNR; q++)
             sum[q] = SMALL ? sum[q] + Vd1[q] + DLd2[q] : __viaddmin_u16x2(__viaddmin_u16x2(sum[q], Vd1[q], kMax2), DLd2[q], kMax2);
         } else if (HAS_V) {
-          const uint32_t lV = sweep_path_core<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
-          const uint32_t lH = sweep_path_core<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
-          group_min2_u16<LPP>(lH, lV, lane, mH, mV);
+          constexpr bool HV = SV_SWEEP_MINPAIR != 0;
+          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+          group_min2_u16<LPP, HV>(lH, lV, lane, mH, mV);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + Vd1[q] : __viaddmin_u16x2(Hs[q], Vd1[q], kMax2);
         } else {
-          sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
         }
 #else
-        sweep_path_step<LPP>(Hs, mH, !on || x == 0, c, kc, gl, lastLane, active, lane);
+        sweep_path_step<LPP>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
         uint32_t sum[kNR];
 #pragma unroll
         for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
@@ -520,12 +541,12 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], Vd1[q], kMax2);
         }
         if (HAS_DL) {
-          sweep_path_step<LPP>(DLd2, mDL, !on || top || x == 0, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(DLd2, mDL, !on || top || xFirst, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DLd2[q], kMax2);
         }
         if (HAS_DR) {
-          sweep_path_step<LPP>(DRin, mDR, !on || top || x == W1 - 1, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(DRin, mDR, !on || top || xLast, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DRin[q], kMax2);
         }
@@ -592,15 +613,21 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         if (gl == 0) __stcg(gOut - gl + 4 * VEC, eMins);
       }
       if (rightGlobal && actL && ((rL % kPub) == kPub - 1 || rL == y1L)) {
-        // publish: the fence makes the entries written so far visible before the counter (it also waits for this warp's
-        // outstanding prefetch loads, which is why it is not done for every row)
-        __threadfence();
+        // publish: the warp barrier orders every lane's entry stores before lane 0's release store of the counter (the
+        // release also waits for the warp's outstanding prefetch loads, which is why it is not done for every row)
         __syncwarp();
-        if (lane == 0) st_relaxed_gpu(gflagOut, rL + 1);
+        if (lane == 0) st_release_gpu(gflagOut, rL + 1);
       }
       __syncwarp();
       if (lane == 0 && actL && hasRight && !rightGlobal) st_flag(&sProg[warp], rL + 1);
-    }
+          };
+      {
+        const int xw = sFirst * kK - T;  // leftmost column of worker 0's chunk; worker j starts (kK + 1) j columns further right
+        const bool interior = T >= RW && T <= H - 2 && xw >= 1 && xw + (kK + 1) * (RW - 1) + kK - 1 <= W1 - 2;
+        if (SV_SWEEP_INTERIOR && interior) phaseB(std::true_type{});
+        else phaseB(std::false_type{});
+      }
+}
 #if SV_SWEEP_PROF
     pfTask += clock64() - pfStart; pfSteps += Tend - Tbeg + 1; pfT0 = clock64();
     if (task < (int)gridDim.x && lane == 0)  // first wave: every strip group starts at the same time
@@ -720,6 +747,7 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.p1dup = dup16((uint32_t)cfg.P1);
   a.p2mp1dup = dup16((uint32_t)(cfg.P2 - cfg.P1));
   a.negp1dup = dup16((uint32_t)(-cfg.P1) & 0xFFFFu);
+  a.one = 1u;
   a.uniqF = 100 - cfg.uniq;
   a.uniqMagic = a.uniqF >= 2 ? (uint32_t)((0x100000000ull + a.uniqF - 1) / a.uniqF) : 0u;
   // MODE_SGBM_3WAY (on stripe frames, see sgbm.cu): left-to-right + top-down in pass 1, right-to-left in pass 2
@@ -739,6 +767,10 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
     a.flip = pass;
     const int paths = pass ? pass2 : pass1;
     const int grid = std::min(nframes * a.G, numSM);
+#if defined(SV_SWEEP_ONLY8)   // quick experiment builds: only the D = 128 MODE_HH throughput kernels are instantiated
+    if (lpp != 8 || paths != 15 || low) return cudaErrorNotSupported;
+    e = pass == 0 ? launch_nw<8, 15, false, kMaxNW>(a, grid, st) : launch_nw<8, 15, true, kMaxNW>(a, grid, st);
+#else
     switch (lpp) {
       case 1: e = launch_lpp<1>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
       case 2: e = launch_lpp<2>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
@@ -746,6 +778,7 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
       case 8: e = launch_lpp<8>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
       default: e = launch_lpp<16>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
     }
+#endif
     if (stats) stats->launches++;
     if (e != cudaSuccess) return e;
   }

@@ -8,6 +8,8 @@ Outputs (committed):
   sgbm_small.npz   small 8UC1 pairs + cv2.StereoSGBM disparities for MODE_SGBM / MODE_HH / MODE_HH4
   bm_small.npz     small pairs + cv2.StereoBM disparities
   stages_small.npz median / filterSpeckles / morph close / remap / reproject / pre-filter chain / resize cases
+  big_sha.npz      sha256 digests of cv2's full-size outputs: 3840x2160 / 256 disparities (gray pair, rectified pair + XYZ,
+                   BGR pair through the whole chain) and 1920x1080 / 128 with the built-in speckle filter
   bottle.npz       the reference's bottle pair (resources/test-images-v1) through the mirror of
                    StereoVision::AnalyzeAndAnnotateImage with Algorithm::kSGBM (src/lib.cpp:53-85):
                    rectified gray inputs of StereoSGBM, raw and post-filtered disparity, calibration
@@ -317,9 +319,77 @@ def save_rectify(path):
     print("wrote", path, os.path.getsize(path), "bytes", [c[0] for c in cases])
 
 
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def big_calib(W, H):
+    """The synthetic single-camera calibration of the full-size tests (same numbers as tests/test_gpu_parity.py)."""
+    K = np.array([[833.77 * 6, 0, 345.2 * 6], [0, 832.87 * 6, 283.1 * 4.5], [0, 0, 1]])
+    dist = np.array([-0.4168, 0.166, 0, 0, 0])
+    P = np.array([[K[0, 0] * 0.9, 0, K[0, 2], 0], [0, K[0, 0] * 0.9, K[1, 2], 0], [0, 0, 1, 0]])
+    Q = np.array([[1, 0, 0, -K[0, 2]], [0, 1, 0, -K[1, 2]], [0, 0, 0, P[0, 0]], [0, 0, 1 / 75.3, 0]])
+    return K, dist, P, Q
+
+
+def save_big(path):
+    """Full-size cases of BASELINE configs 3 and 4, stored as sha256 digests of cv2's outputs (the inputs are regenerated from
+    their seeds by the tests; their digests are stored too, so a synth difference shows up as such).
+      c4_*   3840x2160, 256 disparities, MODE_HH: StereoSGBM on the gray pair; remap -> StereoSGBM -> reprojectImageTo3D
+      c4bgr_* the same size through the reference's whole chain on a BGR pair (src/lib.cpp:53-85 with MODE_HH, D=256)
+      c3spk_* 1920x1080, 128 disparities, MODE_HH with speckleWindowSize=100, speckleRange=2, three pairs"""
+    out = {}
+    H, W, D = 2160, 3840, 256
+    prm = dict(minDisparity=0, numDisparities=D, blockSize=7, P1=392, P2=1568, disp12MaxDiff=1, preFilterCap=32, uniquenessRatio=15,
+               speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_HH)
+    l, r = synth_pair(H, W, D, seed=4)
+    out["c4_in"] = sha(np.stack([l, r]))
+    d = cv_sgbm(l, r, prm)
+    out["c4_disp"] = sha(d)
+    print("c4 direct valid", float((d[:, D:] >= 0).mean()))
+    K, dist, P, Q = big_calib(W, H)
+    m1, m2 = cv2.initUndistortRectifyMap(K, dist, np.eye(3), P, (W, H), cv2.CV_16SC2)
+    lr_, rr_ = cv2.remap(l, m1, m2, cv2.INTER_LINEAR), cv2.remap(r, m1, m2, cv2.INTER_LINEAR)
+    out["c4_rect"] = sha(np.stack([lr_, rr_]))
+    d2 = cv_sgbm(lr_, rr_, prm)
+    out["c4_rect_disp"] = sha(d2)
+    out["c4_rect_xyz"] = sha(cv2.reprojectImageTo3D(d2, Q, handleMissingValues=True))
+    # BGR through the reference's chain
+    lb = np.stack([l, np.roll(l, 1, axis=0) // 2 + 30, 255 - l], axis=2).astype(np.uint8)
+    rb = np.stack([r, np.roll(r, 1, axis=0) // 2 + 30, 255 - r], axis=2).astype(np.uint8)
+    out["c4bgr_in"] = sha(np.stack([lb, rb]))
+    Lr, Rr = cv2.remap(lb, m1, m2, cv2.INTER_LINEAR), cv2.remap(rb, m1, m2, cv2.INTER_LINEAR)
+    k = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32)
+    gl = cv2.filter2D(cv2.cvtColor(cv2.GaussianBlur(Lr, (11, 11), 1.4), cv2.COLOR_BGR2GRAY), -1, k)
+    gr = cv2.filter2D(cv2.cvtColor(cv2.GaussianBlur(Rr, (11, 11), 1.4), cv2.COLOR_BGR2GRAY), -1, k)
+    out["c4bgr_gray"] = sha(np.stack([gl, gr]))
+    raw = cv_sgbm(gl, gr, prm)
+    out["c4bgr_raw"] = sha(raw)
+    post = raw.copy()
+    post[post == -1] = 0
+    cv2.filterSpeckles(post, 0, 150, 32)
+    post = cv2.morphologyEx(post, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (5, 5)))
+    out["c4bgr_post"] = sha(post)
+    out["c4bgr_xyz"] = sha(cv2.reprojectImageTo3D(post, Q, handleMissingValues=True))
+    bf = np.float32(75.3) * np.float32(K[0, 0])
+    out["c4bgr_depth"] = sha(np.where(post > 0, bf / post.astype(np.float32), np.float32(0)).astype(np.float32))
+    print("c4bgr valid", float((raw[:, D:] >= 0).mean()))
+    # 1080p with the speckle filter inside StereoSGBM::compute
+    H, W, D = 1080, 1920, 128
+    prm = dict(prm, numDisparities=D, speckleWindowSize=100, speckleRange=2)
+    for i in range(3):
+        l, r = synth_pair(H, W, D, seed=10 + i)
+        out[f"c3spk_in{i}"] = sha(np.stack([l, r]))
+        d = cv_sgbm(l, r, prm)
+        out[f"c3spk_disp{i}"] = sha(d)
+        out[f"c3_disp{i}"] = sha(cv_sgbm(l, r, dict(prm, speckleWindowSize=0, speckleRange=0)))
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    jobs = dict(sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way)
+    jobs = dict(big_sha=save_big, sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))

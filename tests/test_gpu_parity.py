@@ -379,3 +379,108 @@ def test_sgbm_random_configs_bit_exact(svgpu, oracle, sweep_nw, monkeypatch):
         if nmismatch(got, want):
             bad.append((case, H, W, prm, nmismatch(got, want)))
     assert not bad, bad
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()
+
+
+def _big(key):
+    return golden("big_sha")[key].tobytes()
+
+
+def _big_calib(W, H):
+    K = np.array([[833.77 * 6, 0, 345.2 * 6], [0, 832.87 * 6, 283.1 * 4.5], [0, 0, 1]])
+    dist = np.array([-0.4168, 0.166, 0, 0, 0])
+    P = np.array([[K[0, 0] * 0.9, 0, K[0, 2], 0], [0, K[0, 0] * 0.9, K[1, 2], 0], [0, 0, 1, 0]])
+    Q = np.array([[1, 0, 0, -K[0, 2]], [0, 1, 0, -K[1, 2]], [0, 0, 0, P[0, 0]], [0, 0, 1 / 75.3, 0]])
+    return K, dist, P, Q
+
+
+def test_config4_4k_256_full_frame_sha_vs_cv2(svgpu, oracle):
+    """BASELINE config 4 at full size against cv2's own output (tests/golden/big_sha.npz: sha256 digests written by
+    make_golden.py): 3840x2160, 256 disparities, MODE_HH — (a) svgpu_sgbm_compute on the gray pair, (b) svgpu_pipeline
+    remap -> SGBM -> reprojectImageTo3D on the same pair, (c) a BGR pair through the reference's whole chain
+    (src/lib.cpp:53-85).  Pins the 2160-row vertical / diagonal paths, the 16-lanes-per-pixel reduction and the strip-group
+    hand-over at D = 256."""
+    from svgpu.synth import synth_pair
+    H, W, D = 2160, 3840, 256
+    l, r = synth_pair(H, W, D, seed=4)
+    assert _sha(np.stack([l, r])) == _big("c4_in"), "synthetic input differs from the one the golden digests were made from"
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    K, dist, P, Q = _big_calib(W, H)
+    m1, m2 = oracle.init_undistort_rectify_map(K, dist, np.eye(3), P, (W, H))
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**prm)
+        assert _sha(ctx.sgbm(l, r)) == _big("c4_disp")
+        ctx.set_rectify_maps(0, m1, m2)
+        ctx.set_rectify_maps(1, m1, m2)
+        ctx.set_Q(Q)
+        ctx.set_depth_consts(75.3, float(K[0, 0]))
+        out = ctx.pipeline(l, r, svgpu.STAGE_REMAP | svgpu.STAGE_SGBM | svgpu.STAGE_REPROJECT, want_rect=True, want_xyz=True)
+        assert _sha(np.stack([out["left_rect"], out["right_rect"]])) == _big("c4_rect")
+        assert _sha(out["disp"]) == _big("c4_rect_disp")
+        assert _sha(out["xyz"]) == _big("c4_rect_xyz")
+        lb = np.stack([l, np.roll(l, 1, axis=0) // 2 + 30, 255 - l], axis=2).astype(np.uint8)
+        rb = np.stack([r, np.roll(r, 1, axis=0) // 2 + 30, 255 - r], axis=2).astype(np.uint8)
+        assert _sha(np.stack([lb, rb])) == _big("c4bgr_in")
+        raw = ctx.pipeline(lb, rb, svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM)
+        assert _sha(raw["disp"]) == _big("c4bgr_raw")
+        full = ctx.pipeline(lb, rb, svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM | svgpu.STAGE_POSTFILTER |
+                            svgpu.STAGE_REPROJECT | svgpu.STAGE_DEPTH, want_xyz=True, want_depth=True)
+        assert _sha(full["disp"]) == _big("c4bgr_post")
+        assert _sha(full["xyz"]) == _big("c4bgr_xyz")
+        assert _sha(full["depth"]) == _big("c4bgr_depth")
+
+
+def test_config3_1080p_speckle_batch_and_streaming_vs_cv2(svgpu, oracle):
+    """1920x1080 / 128 / MODE_HH: (a) the speckle filter inside StereoSGBM::compute (speckleWindowSize=100, speckleRange=2)
+    on a batch of three pairs, against cv2's digests and (pair 0) the oracle; (b) the streaming entry point with three
+    overlapping enqueues of two pairs each, results read after sync()."""
+    from svgpu.synth import synth_batch
+    H, W, D = 1080, 1920, 128
+    L, R = synth_batch(3, H, W, D, seed0=10)
+    for i in range(3):
+        assert _sha(np.stack([L[i], R[i]])) == _big(f"c3spk_in{i}")
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    spk = dict(prm, speckleWindowSize=100, speckleRange=2)
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**spk)
+        ctx.reserve(3)
+        got = ctx.sgbm_batch(L, R)
+        for i in range(3):
+            assert _sha(got[i]) == _big(f"c3spk_disp{i}"), i
+        assert nmismatch(got[0], oracle.sgbm(L[0], R[0], **spk)) == 0
+        # streaming: batches (0,1), (1,2), (2,0) in flight together
+        ctx.set_sgbm(**prm)
+        ctx.reserve(2)
+        order = [(0, 1), (1, 2), (2, 0)]
+        ins = [(np.ascontiguousarray(L[list(o)]), np.ascontiguousarray(R[list(o)])) for o in order]
+        outs = [np.zeros((2, H, W), np.int16) for _ in order]
+        for k in range(3):
+            ctx.sgbm_enqueue(ins[k][0], ins[k][1], outs[k])
+        ctx.sync()
+        for k, o in enumerate(order):
+            for q, i in enumerate(o):
+                assert _sha(outs[k][q]) == _big(f"c3_disp{i}"), (k, q)
+
+
+def test_reconfigure_same_cell_count_reallocates(svgpu, oracle):
+    """One context reconfigured between settings whose W1 * D product is equal but whose selection / hand-over buffers are
+    not (W = 320: D = 256 -> W1 = 64, D = 64 -> W1 = 256), and between MODE_SGBM_3WAY and MODE_HH: same output as a fresh
+    context (the scratch is keyed on every buffer's size)."""
+    from svgpu.synth import synth_pair
+    H, W = 40, 320
+    l, r = synth_pair(H, W, 48, seed=7)
+    seq = [dict(REF_PARAMS, numDisparities=256, mode=1), dict(REF_PARAMS, numDisparities=64, mode=1),
+           dict(REF_PARAMS, numDisparities=64, mode=2), dict(REF_PARAMS, numDisparities=128, mode=0),
+           dict(REF_PARAMS, numDisparities=64, mode=3), dict(REF_PARAMS, numDisparities=256, mode=1)]
+    with svgpu.Context(W, H) as ctx:
+        for prm in seq:
+            ctx.set_sgbm(**prm)
+            got = ctx.sgbm(l, r)
+            with svgpu.Context(W, H) as fresh:
+                fresh.set_sgbm(**prm)
+                want = fresh.sgbm(l, r)
+            assert nmismatch(got, want) == 0, prm
+            assert nmismatch(got, oracle.sgbm(l, r, **prm)) == 0, prm
