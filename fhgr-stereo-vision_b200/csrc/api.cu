@@ -43,7 +43,7 @@ struct svgpu_ctx {
   int* minScratch = nullptr;
   // streaming entry point: copy-in / compute / copy-out of consecutive enqueues overlap (double-buffered staging)
   cudaStream_t stIn = nullptr, stOut = nullptr;
-  Buf pipeL[2], pipeR[2], pipeD[2];
+  Buf pipeL[2], pipeR[2], pipeD[2], pipeX[2], pipeZ[2], pipeRL[2], pipeRR[2];
   cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
   unsigned long long enqueued = 0;
 
@@ -221,6 +221,109 @@ int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const
   return SV_OK;
 }
 
+
+// ---- the chain of src/lib.cpp:53-85 on device buffers, n frames --------------------------------------------------
+struct PipeDev {
+  const uint8_t *left, *right;   // n frames of `cn` channels: row strides ls / rs, frame strides lf / rf (bytes)
+  size_t ls, rs, lf, rf;
+  int cn;
+  uint8_t *rectL, *rectR;        // remap output (null: context scratch); filled in with what was used
+  size_t rectS, rectF;
+  int16_t* disp;                 // in (without the SGBM stage) / out
+  size_t dS, dF;
+  float* xyz;                    // null: skipped
+  size_t xS, xF;
+  float* depth;
+  size_t zS, zF;
+};
+
+int pipeline_check(svgpu_ctx* c, int cn, unsigned stages, bool haveDisp) {
+  if (cn != 1 && cn != 3) return fail(c, SV_INVALID_SETTINGS, "channels must be 1 or 3");
+  if ((stages & SV_STAGE_PREFILTER) && cn != 3) return fail(c, SV_INVALID_SETTINGS, "the pre-filter chain needs BGR input");
+  if ((stages & SV_STAGE_SGBM) && !c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
+  if ((stages & SV_STAGE_REMAP) && (!c->map1[0] || !c->map1[1])) return fail(c, SV_NOT_CONFIGURED, "rectify maps not set");
+  if ((stages & SV_STAGE_REPROJECT) && !c->haveQ) return fail(c, SV_NOT_CONFIGURED, "Q not set");
+  if ((stages & SV_STAGE_DEPTH) && !c->haveDepth) return fail(c, SV_NOT_CONFIGURED, "depth constants not set");
+  if ((stages & (SV_STAGE_POSTFILTER | SV_STAGE_REPROJECT | SV_STAGE_DEPTH)) && !(stages & SV_STAGE_SGBM) && !haveDisp)
+    return fail(c, SV_INVALID_IMAGE, "no disparity input");
+  return SV_OK;
+}
+
+int ensure_streams(svgpu_ctx* c) {
+  if (c->stIn) return SV_OK;
+  CU(c, cudaStreamCreateWithFlags(&c->stIn, cudaStreamNonBlocking));
+  CU(c, cudaStreamCreateWithFlags(&c->stOut, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++)
+    for (cudaEvent_t* e : {&c->evIn[s], &c->evComp[s], &c->evOut[s]}) CU(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return SV_OK;
+}
+
+int pipeline_device(svgpu_ctx* c, int n, PipeDev& p, unsigned stages) {
+  const size_t W = c->W, H = c->H;
+  const int cn = p.cn;
+  int rc;
+  const uint8_t *curL = p.left, *curR = p.right;
+  size_t curLs = p.ls, curRs = p.rs, curLf = p.lf, curRf = p.rf;
+  if (stages & SV_STAGE_REMAP) {  // src/lib.cpp:87-94
+    if (!p.rectL || !p.rectR) {
+      rc = ensure(c, c->stRectL, W * H * cn * n); if (rc) return rc;
+      rc = ensure(c, c->stRectR, W * H * cn * n); if (rc) return rc;
+      p.rectL = (uint8_t*)c->stRectL.p; p.rectR = (uint8_t*)c->stRectR.p; p.rectS = W * cn; p.rectF = W * H * cn;
+    }
+    for (int f = 0; f < n; f++) {
+      CU(c, launch_remap(curL + f * curLf, c->W, c->H, curLs, cn, c->map1[0], c->map2[0], p.rectL + f * p.rectF, c->W, c->H, p.rectS, c->st));
+      CU(c, launch_remap(curR + f * curRf, c->W, c->H, curRs, cn, c->map1[1], c->map2[1], p.rectR + f * p.rectF, c->W, c->H, p.rectS, c->st));
+    }
+    c->stats.launches += 2 * n;
+    curL = p.rectL; curR = p.rectR; curLs = curRs = p.rectS; curLf = curRf = p.rectF;
+  }
+  if (stages & SV_STAGE_PREFILTER) {  // src/lib.cpp:231-246
+    rc = ensure(c, c->stTmpH, W * H * 6); if (rc) return rc;
+    rc = ensure(c, c->stTmpG, W * H); if (rc) return rc;
+    rc = ensure(c, c->stGrayL, W * H * n); if (rc) return rc;
+    rc = ensure(c, c->stGrayR, W * H * n); if (rc) return rc;
+    for (int f = 0; f < n; f++) {
+      CU(c, launch_prefilter_chain(curL + f * curLf, curLs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayL.p + f * W * H, W, c->W, c->H, c->st));
+      CU(c, launch_prefilter_chain(curR + f * curRf, curRs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayR.p + f * W * H, W, c->W, c->H, c->st));
+    }
+    c->stats.launches += 6 * n;
+    curL = (uint8_t*)c->stGrayL.p; curR = (uint8_t*)c->stGrayR.p; curLs = curRs = W; curLf = curRf = W * H;
+  }
+  if (stages & SV_STAGE_SGBM) {
+    // without the pre-filter chain a BGR pair goes to StereoSGBM as it is (cv::StereoSGBM::compute on 8UC3 images)
+    rc = run_sgbm(c, n, curL, curLs, curLf, curR, curRs, curRf, p.disp, p.dS, p.dF, (stages & SV_STAGE_PREFILTER) ? 1 : cn); if (rc) return rc;
+  }
+  if (stages & SV_STAGE_POSTFILTER) {
+    // src/lib.cpp:264 is a no-op for SGBM output (invalid = -16, never -1); :265 and :267-268 follow
+    rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;
+    rc = ensure(c, c->stSizes, W * H * 4); if (rc) return rc;
+    rc = ensure(c, c->stDisp2, W * H * 2); if (rc) return rc;
+    for (int f = 0; f < n; f++) {
+      int16_t* dd = (int16_t*)((uint8_t*)p.disp + f * p.dF);
+      int nl = 0;
+      CU(c, launch_filter_speckles(dd, p.dS, c->W, c->H, 0, 150, 32, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl));
+      CU(c, launch_morph_close5(dd, p.dS, (int16_t*)c->stLabels.p, (int16_t*)c->stDisp2.p, W * 2, c->W, c->H, c->st));
+      CU(c, cudaMemcpy2DAsync(dd, p.dS, c->stDisp2.p, W * 2, W * 2, H, cudaMemcpyDeviceToDevice, c->st));
+      c->stats.launches += nl + 2;
+    }
+  }
+  if ((stages & SV_STAGE_REPROJECT) && p.xyz) {  // src/lib.cpp:152-156
+    for (int f = 0; f < n; f++) {
+      int nl = 0;
+      CU(c, launch_reproject((const int16_t*)((const uint8_t*)p.disp + f * p.dF), p.dS, (float*)((uint8_t*)p.xyz + f * p.xF), p.xS, c->W, c->H, c->Qdev, 1,
+                             c->minScratch, c->st, &nl));
+      c->stats.launches += nl;
+    }
+  }
+  if ((stages & SV_STAGE_DEPTH) && p.depth) {  // src/lib.cpp:279-294
+    for (int f = 0; f < n; f++)
+      CU(c, launch_depth((const int16_t*)((const uint8_t*)p.disp + f * p.dF), p.dS, (float*)((uint8_t*)p.depth + f * p.zF), p.zS, c->W, c->H,
+                         c->baseline * c->focal, c->st));
+    c->stats.launches += n;
+  }
+  return SV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,7 +366,7 @@ SVGPU_API int svgpu_destroy(svgpu_ctx* c) {
     release(*b);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (int s = 0; s < 2; s++) {
-    release(c->pipeL[s]); release(c->pipeR[s]); release(c->pipeD[s]);
+    release(c->pipeL[s]); release(c->pipeR[s]); release(c->pipeD[s]); release(c->pipeX[s]); release(c->pipeZ[s]); release(c->pipeRL[s]); release(c->pipeRR[s]);
     for (cudaEvent_t e : {c->evIn[s], c->evComp[s], c->evOut[s]}) if (e) cudaEventDestroy(e);
   }
   if (c->stIn) { cudaStreamSynchronize(c->stIn); cudaStreamDestroy(c->stIn); }
@@ -514,14 +617,9 @@ SVGPU_API int svgpu_sgbm_enqueue_batch(svgpu_ctx* c, int n, const uint8_t* left,
   if (n > c->maxBatch) return fail(c, SV_INVALID_SETTINGS, "enqueue_batch: n exceeds svgpu_reserve()");
   cudaSetDevice(c->device);
   const size_t W = c->W, H = c->H, img = W * H;
-  if (!c->stIn) {
-    CU(c, cudaStreamCreateWithFlags(&c->stIn, cudaStreamNonBlocking));
-    CU(c, cudaStreamCreateWithFlags(&c->stOut, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; s++)
-      for (cudaEvent_t* e : {&c->evIn[s], &c->evComp[s], &c->evOut[s]}) CU(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-  }
+  int rc = ensure_streams(c); if (rc) return rc;
   const int s = (int)(c->enqueued & 1);
-  int rc = ensure(c, c->pipeL[s], img * c->maxBatch); if (rc) return rc;
+  rc = ensure(c, c->pipeL[s], img * c->maxBatch); if (rc) return rc;
   rc = ensure(c, c->pipeR[s], img * c->maxBatch); if (rc) return rc;
   rc = ensure(c, c->pipeD[s], img * 2 * c->maxBatch); if (rc) return rc;
   const bool reused = c->enqueued >= 2;  // slot s was used by the enqueue before the previous one
@@ -739,91 +837,150 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
   SV_STAGE_PROLOGUE();
   if (!io || !io->left || !io->right) return fail(c, SV_INVALID_IMAGE, "empty image");
   const int cn = io->channels;
-  if (cn != 1 && cn != 3) return fail(c, SV_INVALID_SETTINGS, "channels must be 1 or 3");
-  if ((stages & SV_STAGE_PREFILTER) && cn != 3) return fail(c, SV_INVALID_SETTINGS, "the pre-filter chain needs BGR input");
-  if ((stages & SV_STAGE_SGBM) && !c->haveSgbm) return fail(c, SV_NOT_CONFIGURED, "sgbm parameters not set");
-  if ((stages & SV_STAGE_REMAP) && (!c->map1[0] || !c->map1[1])) return fail(c, SV_NOT_CONFIGURED, "rectify maps not set");
-  if ((stages & SV_STAGE_REPROJECT) && !c->haveQ) return fail(c, SV_NOT_CONFIGURED, "Q not set");
-  if ((stages & SV_STAGE_DEPTH) && !c->haveDepth) return fail(c, SV_NOT_CONFIGURED, "depth constants not set");
-  if ((stages & (SV_STAGE_POSTFILTER | SV_STAGE_REPROJECT | SV_STAGE_DEPTH)) && !(stages & SV_STAGE_SGBM) && !io->disp)
-    return fail(c, SV_INVALID_IMAGE, "no disparity input");
+  int rc = pipeline_check(c, cn, stages, io->disp != nullptr);
+  if (rc) return rc;
   const bool host = io->mem == SV_MEM_HOST;
-  int rc;
-  // current left/right images on the device
-  const uint8_t *curL = io->left, *curR = io->right;
-  size_t curLs = io->left_stride, curRs = io->right_stride;
+  PipeDev p{};
+  p.cn = cn;
+  p.left = io->left; p.right = io->right; p.ls = io->left_stride; p.rs = io->right_stride;
   if (host) {
     rc = ensure(c, c->stLeft, W * H * cn); if (rc) return rc;
     rc = ensure(c, c->stRight, W * H * cn); if (rc) return rc;
     rc = h2d_2d(c, c->stLeft.p, W * cn, io->left, io->left_stride, W * cn, (int)H); if (rc) return rc;
     rc = h2d_2d(c, c->stRight.p, W * cn, io->right, io->right_stride, W * cn, (int)H); if (rc) return rc;
-    curL = (uint8_t*)c->stLeft.p; curR = (uint8_t*)c->stRight.p; curLs = curRs = W * cn;
+    p.left = (uint8_t*)c->stLeft.p; p.right = (uint8_t*)c->stRight.p; p.ls = p.rs = W * cn;
   }
-  if (stages & SV_STAGE_REMAP) {
-    uint8_t *oL, *oR; size_t os;
-    if (!host && io->left_rect && io->right_rect) { oL = io->left_rect; oR = io->right_rect; os = io->rect_stride; }
-    else {
-      rc = ensure(c, c->stRectL, W * H * cn); if (rc) return rc;
-      rc = ensure(c, c->stRectR, W * H * cn); if (rc) return rc;
-      oL = (uint8_t*)c->stRectL.p; oR = (uint8_t*)c->stRectR.p; os = W * cn;
-    }
-    CU(c, launch_remap(curL, c->W, c->H, curLs, cn, c->map1[0], c->map2[0], oL, c->W, c->H, os, c->st));
-    CU(c, launch_remap(curR, c->W, c->H, curRs, cn, c->map1[1], c->map2[1], oR, c->W, c->H, os, c->st));
-    c->stats.launches += 2;
-    curL = oL; curR = oR; curLs = curRs = os;
-    if (host && io->left_rect) { rc = d2h_2d(c, io->left_rect, io->rect_stride, oL, os, W * cn, (int)H); if (rc) return rc; }
-    if (host && io->right_rect) { rc = d2h_2d(c, io->right_rect, io->rect_stride, oR, os, W * cn, (int)H); if (rc) return rc; }
-  }
-  if (stages & SV_STAGE_PREFILTER) {
-    rc = ensure(c, c->stTmpH, W * H * 6); if (rc) return rc;
-    rc = ensure(c, c->stTmpG, W * H); if (rc) return rc;
-    rc = ensure(c, c->stGrayL, W * H); if (rc) return rc;
-    rc = ensure(c, c->stGrayR, W * H); if (rc) return rc;
-    CU(c, launch_prefilter_chain(curL, curLs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayL.p, W, c->W, c->H, c->st));
-    CU(c, launch_prefilter_chain(curR, curRs, (uint16_t*)c->stTmpH.p, (uint8_t*)c->stTmpG.p, (uint8_t*)c->stGrayR.p, W, c->W, c->H, c->st));
-    c->stats.launches += 6;
-    curL = (uint8_t*)c->stGrayL.p; curR = (uint8_t*)c->stGrayR.p; curLs = curRs = W;
-  }
-  int16_t* dd = io->disp; size_t dds = io->disp_stride;
-  if (host || !dd) {
+  if (!host && io->left_rect && io->right_rect) { p.rectL = io->left_rect; p.rectR = io->right_rect; p.rectS = io->rect_stride; }
+  p.disp = io->disp; p.dS = io->disp_stride;
+  if (host || !p.disp) {
     rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
     if (host && io->disp && !(stages & SV_STAGE_SGBM)) { rc = h2d_2d(c, c->stDisp.p, W * 2, io->disp, io->disp_stride, W * 2, (int)H); if (rc) return rc; }
-    dd = (int16_t*)c->stDisp.p; dds = W * 2;
-  }
-  if (stages & SV_STAGE_SGBM) {
-    // without the pre-filter chain a BGR pair goes to StereoSGBM as it is (cv::StereoSGBM::compute on 8UC3 images)
-    rc = run_sgbm(c, 1, curL, curLs, 0, curR, curRs, 0, dd, dds, 0, (stages & SV_STAGE_PREFILTER) ? 1 : cn); if (rc) return rc;
-  }
-  if (stages & SV_STAGE_POSTFILTER) {
-    // src/lib.cpp:264 is a no-op for SGBM output (invalid = -16, never -1); :265 and :267-268 follow
-    rc = ensure(c, c->stLabels, W * H * 4); if (rc) return rc;
-    rc = ensure(c, c->stSizes, W * H * 4); if (rc) return rc;
-    rc = ensure(c, c->stDisp2, W * H * 2); if (rc) return rc;
-    int nl = 0;
-    CU(c, launch_filter_speckles(dd, dds, c->W, c->H, 0, 150, 32, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl));
-    CU(c, launch_morph_close5(dd, dds, (int16_t*)c->stLabels.p, (int16_t*)c->stDisp2.p, W * 2, c->W, c->H, c->st));
-    CU(c, cudaMemcpy2DAsync(dd, dds, c->stDisp2.p, W * 2, W * 2, H, cudaMemcpyDeviceToDevice, c->st));
-    c->stats.launches += nl + 2;
-  }
-  if (host && io->disp && (stages & (SV_STAGE_SGBM | SV_STAGE_POSTFILTER))) {
-    rc = d2h_2d(c, io->disp, io->disp_stride, dd, dds, W * 2, (int)H); if (rc) return rc;
+    p.disp = (int16_t*)c->stDisp.p; p.dS = W * 2;
   }
   if ((stages & SV_STAGE_REPROJECT) && io->xyz) {
-    float* o = io->xyz; size_t os = io->xyz_stride;
-    if (host) { rc = ensure(c, c->stXyz, W * H * 12); if (rc) return rc; o = (float*)c->stXyz.p; os = W * 12; }
-    int nl = 0;
-    CU(c, launch_reproject(dd, dds, o, os, c->W, c->H, c->Qdev, 1, c->minScratch, c->st, &nl));
-    c->stats.launches += nl;
-    if (host) { rc = d2h_2d(c, io->xyz, io->xyz_stride, o, os, W * 12, (int)H); if (rc) return rc; }
+    p.xyz = io->xyz; p.xS = io->xyz_stride;
+    if (host) { rc = ensure(c, c->stXyz, W * H * 12); if (rc) return rc; p.xyz = (float*)c->stXyz.p; p.xS = W * 12; }
   }
   if ((stages & SV_STAGE_DEPTH) && io->depth) {
-    float* o = io->depth; size_t os = io->depth_stride;
-    if (host) { rc = ensure(c, c->stDepth, W * H * 4); if (rc) return rc; o = (float*)c->stDepth.p; os = W * 4; }
-    CU(c, launch_depth(dd, dds, o, os, c->W, c->H, c->baseline * c->focal, c->st));
-    c->stats.launches++;
-    if (host) { rc = d2h_2d(c, io->depth, io->depth_stride, o, os, W * 4, (int)H); if (rc) return rc; }
+    p.depth = io->depth; p.zS = io->depth_stride;
+    if (host) { rc = ensure(c, c->stDepth, W * H * 4); if (rc) return rc; p.depth = (float*)c->stDepth.p; p.zS = W * 4; }
+  }
+  rc = pipeline_device(c, 1, p, stages);
+  if (rc) return rc;
+  if (!host) return SV_OK;
+  if (stages & SV_STAGE_REMAP) {
+    if (io->left_rect) { rc = d2h_2d(c, io->left_rect, io->rect_stride, p.rectL, p.rectS, W * cn, (int)H); if (rc) return rc; }
+    if (io->right_rect) { rc = d2h_2d(c, io->right_rect, io->rect_stride, p.rectR, p.rectS, W * cn, (int)H); if (rc) return rc; }
+  }
+  if (io->disp && (stages & (SV_STAGE_SGBM | SV_STAGE_POSTFILTER))) {
+    rc = d2h_2d(c, io->disp, io->disp_stride, p.disp, p.dS, W * 2, (int)H); if (rc) return rc;
+  }
+  if (p.xyz) { rc = d2h_2d(c, io->xyz, io->xyz_stride, p.xyz, p.xS, W * 12, (int)H); if (rc) return rc; }
+  if (p.depth) { rc = d2h_2d(c, io->depth, io->depth_stride, p.depth, p.zS, W * 4, (int)H); if (rc) return rc; }
+  return check_status(c);
+}
+
+SVGPU_API int svgpu_pipeline_batch(svgpu_ctx* c, int n, const svgpu_pipeline_batch_io* io, unsigned stages) {
+  SV_STAGE_PROLOGUE();
+  if (!io || !io->left || !io->right || n <= 0) return fail(c, SV_INVALID_IMAGE, "empty batch");
+  const int cn = io->channels;
+  int rc = pipeline_check(c, cn, stages, io->disp != nullptr);
+  if (rc) return rc;
+  if (!io->disp) return fail(c, SV_INVALID_IMAGE, "the batch calls need a disparity buffer");
+  const bool host = io->mem == SV_MEM_HOST;
+  const size_t px = W * H, img = px * cn;
+  const int chunk = c->maxBatch;
+  const bool wantRect = (stages & SV_STAGE_REMAP) && io->left_rect && io->right_rect;
+  const bool wantXyz = (stages & SV_STAGE_REPROJECT) && io->xyz, wantDepth = (stages & SV_STAGE_DEPTH) && io->depth;
+  if (host) {
+    rc = ensure(c, c->stLeft, img * chunk); if (rc) return rc;
+    rc = ensure(c, c->stRight, img * chunk); if (rc) return rc;
+    rc = ensure(c, c->stDisp, px * 2 * chunk); if (rc) return rc;
+    if (wantXyz) { rc = ensure(c, c->stXyz, px * 12 * chunk); if (rc) return rc; }
+    if (wantDepth) { rc = ensure(c, c->stDepth, px * 4 * chunk); if (rc) return rc; }
+  }
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int m = std::min(chunk, n - f0);
+    PipeDev p{};
+    p.cn = cn; p.ls = p.rs = W * cn; p.lf = p.rf = img;
+    p.dS = W * 2; p.dF = px * 2; p.xS = W * 12; p.xF = px * 12; p.zS = W * 4; p.zF = px * 4;
+    if (host) {
+      CU(c, cudaMemcpyAsync(c->stLeft.p, io->left + f0 * img, img * m, cudaMemcpyHostToDevice, c->st));
+      CU(c, cudaMemcpyAsync(c->stRight.p, io->right + f0 * img, img * m, cudaMemcpyHostToDevice, c->st));
+      if (!(stages & SV_STAGE_SGBM)) CU(c, cudaMemcpyAsync(c->stDisp.p, io->disp + f0 * px, px * 2 * m, cudaMemcpyHostToDevice, c->st));
+      p.left = (uint8_t*)c->stLeft.p; p.right = (uint8_t*)c->stRight.p; p.disp = (int16_t*)c->stDisp.p;
+      if (wantXyz) p.xyz = (float*)c->stXyz.p;
+      if (wantDepth) p.depth = (float*)c->stDepth.p;
+    } else {
+      p.left = io->left + f0 * img; p.right = io->right + f0 * img; p.disp = io->disp + f0 * px;
+      if (wantRect) { p.rectL = io->left_rect + f0 * img; p.rectR = io->right_rect + f0 * img; p.rectS = W * cn; p.rectF = img; }
+      if (wantXyz) p.xyz = io->xyz + f0 * px * 3;
+      if (wantDepth) p.depth = io->depth + f0 * px;
+    }
+    rc = pipeline_device(c, m, p, stages);
+    if (rc) return rc;
+    if (host) {
+      if (wantRect) {
+        CU(c, cudaMemcpyAsync(io->left_rect + f0 * img, p.rectL, img * m, cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaMemcpyAsync(io->right_rect + f0 * img, p.rectR, img * m, cudaMemcpyDeviceToHost, c->st));
+      }
+      if (stages & (SV_STAGE_SGBM | SV_STAGE_POSTFILTER)) CU(c, cudaMemcpyAsync(io->disp + f0 * px, p.disp, px * 2 * m, cudaMemcpyDeviceToHost, c->st));
+      if (wantXyz) CU(c, cudaMemcpyAsync(io->xyz + f0 * px * 3, p.xyz, px * 12 * m, cudaMemcpyDeviceToHost, c->st));
+      if (wantDepth) CU(c, cudaMemcpyAsync(io->depth + f0 * px, p.depth, px * 4 * m, cudaMemcpyDeviceToHost, c->st));
+    }
   }
   if (host) return check_status(c);
+  return SV_OK;
+}
+
+SVGPU_API int svgpu_pipeline_enqueue_batch(svgpu_ctx* c, int n, const svgpu_pipeline_batch_io* io, unsigned stages) {
+  SV_STAGE_PROLOGUE();
+  if (!io || !io->left || !io->right || n <= 0) return fail(c, SV_INVALID_IMAGE, "empty batch");
+  if (io->mem != SV_MEM_HOST) return fail(c, SV_INVALID_SETTINGS, "pipeline_enqueue_batch takes host buffers");
+  if (n > c->maxBatch) return fail(c, SV_INVALID_SETTINGS, "pipeline_enqueue_batch: n exceeds svgpu_reserve()");
+  const int cn = io->channels;
+  int rc = pipeline_check(c, cn, stages, io->disp != nullptr);
+  if (rc) return rc;
+  if (!io->disp) return fail(c, SV_INVALID_IMAGE, "the batch calls need a disparity buffer");
+  rc = ensure_streams(c); if (rc) return rc;
+  const size_t px = W * H, img = px * cn, cap = (size_t)c->maxBatch;
+  const bool wantRect = (stages & SV_STAGE_REMAP) && io->left_rect && io->right_rect;
+  const bool wantXyz = (stages & SV_STAGE_REPROJECT) && io->xyz, wantDepth = (stages & SV_STAGE_DEPTH) && io->depth;
+  const int s = (int)(c->enqueued & 1);
+  rc = ensure(c, c->pipeL[s], img * cap); if (rc) return rc;
+  rc = ensure(c, c->pipeR[s], img * cap); if (rc) return rc;
+  rc = ensure(c, c->pipeD[s], px * 2 * cap); if (rc) return rc;
+  if (wantRect) { rc = ensure(c, c->pipeRL[s], img * cap); if (rc) return rc; rc = ensure(c, c->pipeRR[s], img * cap); if (rc) return rc; }
+  if (wantXyz) { rc = ensure(c, c->pipeX[s], px * 12 * cap); if (rc) return rc; }
+  if (wantDepth) { rc = ensure(c, c->pipeZ[s], px * 4 * cap); if (rc) return rc; }
+  const bool reused = c->enqueued >= 2;  // slot s was used by the enqueue before the previous one
+  if (reused) CU(c, cudaStreamWaitEvent(c->stIn, c->evComp[s], 0));
+  CU(c, cudaMemcpyAsync(c->pipeL[s].p, io->left, img * n, cudaMemcpyHostToDevice, c->stIn));
+  CU(c, cudaMemcpyAsync(c->pipeR[s].p, io->right, img * n, cudaMemcpyHostToDevice, c->stIn));
+  if (!(stages & SV_STAGE_SGBM)) CU(c, cudaMemcpyAsync(c->pipeD[s].p, io->disp, px * 2 * n, cudaMemcpyHostToDevice, c->stIn));
+  CU(c, cudaEventRecord(c->evIn[s], c->stIn));
+  CU(c, cudaStreamWaitEvent(c->st, c->evIn[s], 0));
+  if (reused) CU(c, cudaStreamWaitEvent(c->st, c->evOut[s], 0));
+  PipeDev p{};
+  p.cn = cn; p.ls = p.rs = W * cn; p.lf = p.rf = img;
+  p.left = (uint8_t*)c->pipeL[s].p; p.right = (uint8_t*)c->pipeR[s].p;
+  p.disp = (int16_t*)c->pipeD[s].p; p.dS = W * 2; p.dF = px * 2;
+  if (wantRect) { p.rectL = (uint8_t*)c->pipeRL[s].p; p.rectR = (uint8_t*)c->pipeRR[s].p; p.rectS = W * cn; p.rectF = img; }
+  if (wantXyz) { p.xyz = (float*)c->pipeX[s].p; p.xS = W * 12; p.xF = px * 12; }
+  if (wantDepth) { p.depth = (float*)c->pipeZ[s].p; p.zS = W * 4; p.zF = px * 4; }
+  rc = pipeline_device(c, n, p, stages);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->evComp[s], c->st));
+  CU(c, cudaStreamWaitEvent(c->stOut, c->evComp[s], 0));
+  if (wantRect) {
+    CU(c, cudaMemcpyAsync(io->left_rect, p.rectL, img * n, cudaMemcpyDeviceToHost, c->stOut));
+    CU(c, cudaMemcpyAsync(io->right_rect, p.rectR, img * n, cudaMemcpyDeviceToHost, c->stOut));
+  }
+  if (stages & (SV_STAGE_SGBM | SV_STAGE_POSTFILTER)) CU(c, cudaMemcpyAsync(io->disp, p.disp, px * 2 * n, cudaMemcpyDeviceToHost, c->stOut));
+  if (wantXyz) CU(c, cudaMemcpyAsync(io->xyz, p.xyz, px * 12 * n, cudaMemcpyDeviceToHost, c->stOut));
+  if (wantDepth) CU(c, cudaMemcpyAsync(io->depth, p.depth, px * 4 * n, cudaMemcpyDeviceToHost, c->stOut));
+  CU(c, cudaEventRecord(c->evOut[s], c->stOut));
+  c->enqueued++;
   return SV_OK;
 }
 

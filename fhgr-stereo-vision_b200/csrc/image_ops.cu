@@ -169,9 +169,11 @@ __global__ void __launch_bounds__(256) k_reproject(const int16_t* __restrict__ d
 #pragma unroll
   for (int r = 0; r < 4; r++) h[r] = Q[r * 4 + 0] * x + Q[r * 4 + 1] * y + Q[r * 4 + 2] * d + Q[r * 4 + 3];
   float* o = (float*)((uint8_t*)xyz + (size_t)y * xstride) + (size_t)x * 3;
-  o[0] = (float)((double)(float)h[0] / h[3]);
-  o[1] = (float)((double)(float)h[1] / h[3]);
-  float z = (float)((double)(float)h[2] / h[3]);
+  // Vec3f /= double in OpenCV multiplies by the reciprocal; explicit round-to-nearest operations (no contraction)
+  const double iw = __ddiv_rn(1.0, h[3]);
+  o[0] = (float)__dmul_rn((double)(float)h[0], iw);
+  o[1] = (float)__dmul_rn((double)(float)h[1], iw);
+  float z = (float)__dmul_rn((double)(float)h[2], iw);
   if (handleMissing && di == *minDisp) z = 10000.f;
   o[2] = z;
 }

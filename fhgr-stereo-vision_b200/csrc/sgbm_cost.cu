@@ -27,6 +27,9 @@
 #ifndef SV_COST_COLS
 #define SV_COST_COLS 1
 #endif
+#ifndef SV_COST_MINB
+#define SV_COST_MINB SV_COST_COLS   // CTAs per SM the register allocation is bounded for (threads per CTA = 512 / COLS)
+#endif
 
 namespace svgpu {
 
@@ -43,7 +46,7 @@ template <int NC, int RB, int CH>
 __host__ __device__ inline CostGeom cost_geom(int D) {
   CostGeom g;
   g.ng = D / kDPL;
-  g.NJ = NC + D - 9;
+  g.NJ = (NC + D - 9 + 1) & ~1;   // even: the records of even and odd positions form two planes when a thread owns two columns
   g.rowU4 = NC + 1;
   g.offL = 0;                                        // [2 rows][CH planes][NC] uint4
   g.offR = g.offL + (size_t)2 * CH * NC * 16;        // [2 rows][CH planes][NJ] uint4
@@ -62,7 +65,7 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
 // COLS neighbouring columns per thread: 8 of the 9 right-image records of two neighbouring columns are the same,
 // so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
 template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
-__global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
+__global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1 : SV_COST_MINB) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
                                                                 uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4,
                                                                 int planeRows, int rowsOut) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
@@ -93,6 +96,10 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
   // position of tile column c inside a line of the Vs buffer: the columns of one thread go to different planes so
   // that the lanes of a warp store neighbouring words
   auto vpos = [](int c) { return COLS == 1 ? c : (c % COLS) * NCP + c / COLS; };
+  // the same for the staged records: a thread reads the records of COLS neighbouring columns / positions, so even and odd
+  // ones live in separate planes and the lanes of a warp read neighbouring 16-byte words of one plane
+  auto lpos = [](int c) { return COLS == 1 ? c : (c % COLS) * NCP + c / COLS; };
+  auto rpos = [NJ](int j) { return COLS == 1 ? j : (j % COLS) * (NJ / COLS) + j / COLS; };
   // ---- horizontal mapping: lanes = (half-group, row), threads of one lane slot walk a run of columns.  The window
   //      replicates the border columns of the volume (A.4): indices are clamped to the columns of x' = 0 .. W1-1
   const int gh = tid % (ng * 2), hrow = (tid / (ng * 2)) % RB, run = tid / (ng * 2 * RB);
@@ -114,14 +121,14 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
       const int ch = it / NC, cc = it % NC;
       // columns outside the volume are computed on some valid pixel and ignored by the horizontal phase
       itOffA[q] = ch * Wp + min(max(x0 - R + cc + cfg.minX1, 0), cfg.W - 1);
-      itDst[q] = ch * NC + cc;
+      itDst[q] = ch * NC + lpos(cc);
       itLeft |= 1u << q;
     } else if (it < CH * NC + CH * NJ) {
       const int k = it - CH * NC, ch = k / NJ, j = k % NJ;
       // positions outside the image only ever pair with cells outside the volume: any in-range word will do
       itOffA[q] = ch * Wp + min(max(xrMax - j, 0), cfg.W - 1);
       itOffB[q] = ch * Wp + min(max(xrMax - j - 8, 0), cfg.W - 1);
-      itDst[q] = ch * NJ + j;
+      itDst[q] = ch * NJ + rpos(j);
     }
   }
   uint2 stA[ITEMS], stB[ITEMS];
@@ -188,14 +195,14 @@ __global__ void __launch_bounds__(512 / COLS, COLS) k_cost_tile(const uint2* __r
       if (yy != computed) {
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) {
-          const uint4* lrec = sL + ((yy & 1) * CH + ch) * NC + c0;
-          const uint4* rrec = sR + ((yy & 1) * CH + ch) * NJ + j0;
+          const uint4* lrec = sL + ((yy & 1) * CH + ch) * NC;
+          const uint4* rrec = sR + ((yy & 1) * CH + ch) * NJ;
           uint4 lu[COLS];
 #pragma unroll
-          for (int m = 0; m < COLS; m++) lu[m] = lrec[m];
+          for (int m = 0; m < COLS; m++) lu[m] = lrec[lpos(c0 + m)];
 #pragma unroll
           for (int q = 0; q < kNR + COLS - 1; q++) {
-            const uint4 rr = rrec[q];
+            const uint4 rr = rrec[rpos(j0 + q)];
 #pragma unroll
             for (int m = 0; m < COLS; m++) {
               const int i = q - (COLS - 1 - m);
@@ -321,7 +328,13 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes
 #if SV_COST_COLS == 2
   // two columns per thread, 32 column pairs x D/16 groups <= 256 threads, two CTAs per SM
   if (cfg.D > 128) return launch_cost_r<32, 2, 4, 3>(cfg, sc, nframes, st);   // 16 pairs x <= 16 groups
-  if (cfg.D == 128) return launch_cost_r<64, 2, 4, 2>(cfg, sc, nframes, st);
+#ifndef SV_COST_NC
+#define SV_COST_NC 64
+#endif
+#ifndef SV_COST_RB
+#define SV_COST_RB 4
+#endif
+  if (cfg.D == 128) return launch_cost_r<SV_COST_NC, 2, SV_COST_RB, 2>(cfg, sc, nframes, st);
   if (cfg.D >= 64) return launch_cost_r<64, 2, 4, 3>(cfg, sc, nframes, st);
   return launch_cost_r<64, 2, 4, 9>(cfg, sc, nframes, st);
 #else

@@ -22,13 +22,13 @@ __host__ __device__ __forceinline__ int vol_index(int d) { return (d & ~15) | ((
 
 // compile-time tuning knobs of the path step (tools/build_variants.sh builds alternatives for A/B runs on the GPU)
 #ifndef SV_SWEEP_EDGEMAD
-#define SV_SWEEP_EDGEMAD 0   // 1: the MAX_COST neighbours of a worker's first / last lane through a multiply-add (FMA pipe) instead of a select (ALU pipe)
+#define SV_SWEEP_EDGEMAD 1   // 1: the MAX_COST neighbours of a worker's first / last lane through a multiply-add (FMA pipe) instead of a select (ALU pipe)
 #endif
 #ifndef SV_SWEEP_FMAADD
 #define SV_SWEEP_FMAADD 0    // n: the first n paths of a pixel form y + C - m with two multiply-adds (FMA pipe) instead of one three-input add (ALU pipe)
 #endif
 #ifndef SV_SWEEP_MINPAIR
-#define SV_SWEEP_MINPAIR 0   // 1: paired path minima fold the two halves of the lane minimum while packing (2 instructions fewer per pair)
+#define SV_SWEEP_MINPAIR 1   // 1: paired path minima fold the two halves of the lane minimum while packing (2 instructions fewer per pair)
 #endif
 
 struct SweepK {

@@ -67,7 +67,10 @@ namespace {
 #define SV_SWEEP_MIN2 1      // 1: the minima of two paths share one shuffle butterfly, 0: one butterfly per path
 #endif
 #ifndef SV_SWEEP_INTERIOR
-#define SV_SWEEP_INTERIOR 1  // 1: separate copy of the chunk code for warps whose pixels all lie strictly inside the volume
+#define SV_SWEEP_INTERIOR 0  // 1: separate copy of the chunk code for warps whose pixels all lie strictly inside the volume
+#endif
+#ifndef SV_SWEEP_PIXFENCE
+#define SV_SWEEP_PIXFENCE 0  // 1: compiler-level memory fence between the pixels of a chunk (keeps their loads / stores from being batched)
 #endif
 #ifndef SV_SWEEP_FAKE
 #define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       uint4 eMins = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int i = 0; i < kK; i++) {
+        if (SV_SWEEP_PIXFENCE && i > 0) asm volatile("" ::: "memory");
         const int x = xl + i;
         const bool on = IN || (act && (unsigned)x < (unsigned)W1);
         const bool xFirst = !IN && x == 0, xLast = !IN && x == W1 - 1;

@@ -27,6 +27,7 @@ EXPORTS = (
     "svgpu_prefilter_chain", "svgpu_resize", "svgpu_pipeline", "svgpu_debug_copy_volume", "svgpu_launch_count",
     "svgpu_enable_stage_timing", "svgpu_last_stage_ms", "svgpu_debug_keep_volume",
     "svgpu_init_rectify_maps", "svgpu_get_rectify_maps", "svgpu_stereo_rectify",
+    "svgpu_pipeline_batch", "svgpu_pipeline_enqueue_batch",
 )
 
 
@@ -49,6 +50,12 @@ class PipelineIO(C.Structure):
         ("channels", C.c_int), ("left_rect", C.c_void_p), ("right_rect", C.c_void_p), ("rect_stride", C.c_size_t),
         ("disp", C.c_void_p), ("disp_stride", C.c_size_t), ("xyz", C.c_void_p), ("xyz_stride", C.c_size_t),
         ("depth", C.c_void_p), ("depth_stride", C.c_size_t), ("mem", C.c_int)]
+
+
+class PipelineBatchIO(C.Structure):
+    _fields_ = [
+        ("left", C.c_void_p), ("right", C.c_void_p), ("channels", C.c_int), ("left_rect", C.c_void_p), ("right_rect", C.c_void_p),
+        ("disp", C.c_void_p), ("xyz", C.c_void_p), ("depth", C.c_void_p), ("mem", C.c_int)]
 
 
 class SvgpuError(RuntimeError):
@@ -101,6 +108,8 @@ def load():
         "svgpu_prefilter_chain": (i, [vp, vp, sz, vp, sz, i]),
         "svgpu_resize": (i, [vp, vp, i, i, sz, i, vp, sz, i]),
         "svgpu_pipeline": (i, [vp, C.POINTER(PipelineIO), C.c_uint]),
+        "svgpu_pipeline_batch": (i, [vp, i, C.POINTER(PipelineBatchIO), C.c_uint]),
+        "svgpu_pipeline_enqueue_batch": (i, [vp, i, C.POINTER(PipelineBatchIO), C.c_uint]),
         "svgpu_debug_copy_volume": (i, [vp, i, vp, sz]),
         "svgpu_launch_count": (C.c_longlong, [vp]),
         "svgpu_enable_stage_timing": (i, [vp, i]),

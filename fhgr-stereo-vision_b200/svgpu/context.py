@@ -27,6 +27,7 @@ class Context:
             raise _abi.SvgpuError(rc, "svgpu_create failed (no CUDA device of compute capability 10.x, or out of memory)")
         self._h = h
         self._keep = []
+        self._user_stream = False
 
     # -- plumbing ------------------------------------------------------------------------------
     def close(self):
@@ -54,12 +55,19 @@ class Context:
     def _ptr(a):
         return C.c_void_p(a.data_ptr()) if _is_tensor(a) else a.ctypes.data_as(C.c_void_p)
 
-    @staticmethod
-    def _mem(*arrays):
+    def _mem(self, *arrays):
         dev = [_is_tensor(a) for a in arrays if a is not None]
         if any(dev) and not all(dev):
             raise ValueError("mix of host (numpy) and device (torch) buffers")
-        return _abi.SV_MEM_DEVICE if dev and dev[0] else _abi.SV_MEM_HOST
+        if dev and dev[0]:
+            # Device tensors live on torch's streams: unless the caller attached a stream of their own, the call runs on torch's
+            # current stream, so that it is ordered after the producers of its inputs and before the consumers of its outputs
+            # (and torch's caching allocator sees the use).
+            if not self._user_stream:
+                import torch
+                self._lib.svgpu_set_stream(self._h, C.c_void_p(int(torch.cuda.current_stream(self.device).cuda_stream)))
+            return _abi.SV_MEM_DEVICE
+        return _abi.SV_MEM_HOST
 
     @staticmethod
     def _stride(a):
@@ -89,9 +97,12 @@ class Context:
     def set_stream(self, cuda_stream):
         """Run on the caller's cudaStream_t handle (an int; 0 is the CUDA default stream)."""
         self._check(self._lib.svgpu_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+        self._user_stream = True
 
     def use_own_stream(self):
+        """Back to the context's private stream for host-memory calls; calls on device tensors follow torch's current stream."""
         self._check(self._lib.svgpu_use_own_stream(self._h))
+        self._user_stream = False
 
     def reserve(self, max_batch):
         self._check(self._lib.svgpu_reserve(self._h, int(max_batch)))
@@ -196,6 +207,11 @@ class Context:
         if tuple(left.shape[1:]) != (self.height, self.width) or tuple(right.shape) != tuple(left.shape):
             raise ValueError("batch must be [n][H][W] 8UC1")
         disp = out if out is not None else self._out_like(left, (n, self.height, self.width), np.int16)
+        if out is not None:
+            if _is_tensor(out) != _is_tensor(left) or tuple(out.shape) != (n, self.height, self.width):
+                raise ValueError("out must be [n][H][W] int16 in the same memory as the inputs")
+            if (str(out.dtype) != "torch.int16" or not out.is_contiguous()) if _is_tensor(out) else (out.dtype != np.int16 or not out.flags["C_CONTIGUOUS"]):
+                raise ValueError("out must be a contiguous int16 array")
         self._check(self._lib.svgpu_sgbm_compute_batch(self._h, n, self._ptr(left), self._ptr(right), self._ptr(disp),
                                                        self._mem(left, right, disp)))
         return disp
@@ -313,6 +329,65 @@ class Context:
             io.depth, io.depth_stride = self._ptr(out["depth"]), self._stride(out["depth"])
         self._check(self._lib.svgpu_pipeline(self._h, C.byref(io), int(stages)))
         return out
+
+    def _batch_io(self, left, right, stages, want_rect, want_xyz, want_depth, out, disp_in):
+        """Fills a svgpu_pipeline_batch_io for tightly packed [n][H][W](x cn) frames; `out` may carry preallocated result arrays."""
+        if _is_tensor(left):
+            if not (left.is_contiguous() and right.is_contiguous()):
+                raise ValueError("batch tensors must be contiguous")
+        else:
+            left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+        H, W = self.height, self.width
+        n = int(left.shape[0])
+        cn = 1 if len(left.shape) == 3 else int(left.shape[3])
+        want = (n, H, W) if cn == 1 else (n, H, W, cn)
+        if tuple(left.shape) != want or tuple(right.shape) != want:
+            raise ValueError("batch must be [n][H][W] 8UC1 or [n][H][W][3] 8UC3 of the context size")
+        out = dict(out or {})
+        io = _abi.PipelineBatchIO()
+        io.left, io.right, io.channels = self._ptr(left), self._ptr(right), cn
+        io.mem = self._mem(left, right)
+
+        def buf(key, shape, dtype):
+            a = out.get(key)
+            if a is None:
+                a = out[key] = self._out_like(left, shape, dtype)
+            else:
+                ok = tuple(a.shape) == tuple(shape) and (a.is_contiguous() if _is_tensor(a) else (a.flags["C_CONTIGUOUS"] and a.dtype == dtype))
+                if not ok or _is_tensor(a) != _is_tensor(left):
+                    raise ValueError(f"output '{key}' must be a contiguous {np.dtype(dtype).name} array of shape {tuple(shape)} in the same memory as the inputs")
+            return self._ptr(a)
+
+        if want_rect:
+            io.left_rect, io.right_rect = buf("left_rect", want, np.uint8), buf("right_rect", want, np.uint8)
+        if disp_in is not None:
+            out["disp"] = disp_in if _is_tensor(disp_in) else np.ascontiguousarray(disp_in, np.int16)
+        io.disp = buf("disp", (n, H, W), np.int16)
+        if want_xyz:
+            io.xyz = buf("xyz", (n, H, W, 3), np.float32)
+        if want_depth:
+            io.depth = buf("depth", (n, H, W), np.float32)
+        return n, io, out, (left, right)
+
+    def pipeline_batch(self, left, right, stages, want_rect=False, want_xyz=False, want_depth=False, out=None, disp=None):
+        """StereoVision::AnalyzeAndAnnotateImage (src/lib.cpp:53-85) for n frames per call (svgpu_pipeline_batch): what the folder
+        and livecam loops (static-image-main.cpp:107-127, livecam-main.cpp:70-106) do frame by frame."""
+        n, io, out, _ = self._batch_io(left, right, stages, want_rect, want_xyz, want_depth, out, disp)
+        self._check(self._lib.svgpu_pipeline_batch(self._h, n, C.byref(io), int(stages)))
+        return out
+
+    def pipeline_enqueue(self, left, right, stages, out, want_rect=False, want_xyz=False, want_depth=False):
+        """Streaming form (svgpu_pipeline_enqueue_batch): host arrays only, returns at once; `out` must hold the preallocated
+        result arrays ('disp' and, as requested, 'left_rect', 'right_rect', 'xyz', 'depth').  Keep everything alive and
+        untouched until sync()."""
+        if _is_tensor(left) or _is_tensor(right):
+            raise ValueError("pipeline_enqueue takes host arrays")
+        if not isinstance(out, dict) or "disp" not in out:
+            raise ValueError("pipeline_enqueue needs preallocated outputs")
+        n, io, out2, ins = self._batch_io(left, right, stages, want_rect, want_xyz, want_depth, out, None)
+        self._keep = getattr(self, "_keep", [])[-8:] + [(ins, out2)]
+        self._check(self._lib.svgpu_pipeline_enqueue_batch(self._h, n, C.byref(io), int(stages)))
+        return out2
 
     def debug_volume(self, which, shape):
         out = np.zeros(shape, np.int16)

@@ -188,6 +188,27 @@ typedef struct svgpu_pipeline_io {
 /* StereoVision::AnalyzeAndAnnotateImage with Algorithm::kSGBM — src/lib.cpp:53-85 */
 SVGPU_API int svgpu_pipeline(svgpu_ctx* ctx, const svgpu_pipeline_io* io, unsigned stages);
 
+/* The same chain for n independent pairs per call: what the folder loop (apps/stereo-vision/static-image-main.cpp:107-127)
+ * and the livecam loop (apps/stereo-vision/livecam-main.cpp:70-106) run once per frame through
+ * StereoVision::AnalyzeAndAnnotateImage (src/lib.cpp:53-85).  Frames are tightly packed. */
+typedef struct svgpu_pipeline_batch_io {
+  const uint8_t* left;  /* [n][height][width][channels] */
+  const uint8_t* right;
+  int channels;         /* 3 (BGR) or 1 */
+  uint8_t* left_rect;   /* optional [n][height][width][channels] (both or neither) */
+  uint8_t* right_rect;
+  int16_t* disp;        /* [n][height][width] CV_16S; input when SV_STAGE_SGBM is not requested */
+  float* xyz;           /* optional [n][height][width][3] */
+  float* depth;         /* optional [n][height][width] */
+  int mem;              /* SV_MEM_HOST or SV_MEM_DEVICE */
+} svgpu_pipeline_batch_io;
+/* n pairs, in chunks of svgpu_reserve() pairs; host buffers: returns when the results are in them */
+SVGPU_API int svgpu_pipeline_batch(svgpu_ctx* ctx, int n, const svgpu_pipeline_batch_io* io, unsigned stages);
+/* Streaming form (host buffers, pinned for real overlap; n <= svgpu_reserve()): returns after enqueueing; copy-in of call
+ * k+1, the kernels of call k and copy-out of call k-1 overlap on three streams.  Buffers must stay untouched until
+ * svgpu_sync(ctx), which also reports errors.  Shares its two staging slots with svgpu_sgbm_enqueue_batch. */
+SVGPU_API int svgpu_pipeline_enqueue_batch(svgpu_ctx* ctx, int n, const svgpu_pipeline_batch_io* io, unsigned stages);
+
 /* ---- test hooks (used by tests/ to diff intermediates against the oracle) ------------- */
 /* copies the cost volume Ctrue (which=0) or the aggregated S (which=1) of pair 0 of the last
  * sgbm call to host: [H][W1][D] int16, disparities in natural order */

@@ -144,7 +144,10 @@ void svo_reproject_s16(const int16_t* disp, int W, int H, const double* Q, int h
       double h[4];
       for (int r = 0; r < 4; r++) h[r] = Q[r * 4 + 0] * x + Q[r * 4 + 1] * y + Q[r * 4 + 2] * d + Q[r * 4 + 3];
       float* o = xyz + ((size_t)y * W + x) * 3;
-      for (int r = 0; r < 3; r++) o[r] = (float)((double)(float)h[r] / h[3]);
+      /* Vec3f /= double multiplies by the reciprocal (cv::Matx operator/=): pinned at full 4K size against cv2, where the
+       * difference to a true division shows in about 1 of 65,000 values */
+      const double iw = 1.0 / h[3];
+      for (int r = 0; r < 3; r++) o[r] = (float)((double)(float)h[r] * iw);
       if (handleMissing && fabs(d - minD) <= FLT_EPSILON) o[2] = 10000.f;
     }
 }

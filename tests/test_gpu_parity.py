@@ -484,3 +484,57 @@ def test_reconfigure_same_cell_count_reallocates(svgpu, oracle):
                 want = fresh.sgbm(l, r)
             assert nmismatch(got, want) == 0, prm
             assert nmismatch(got, oracle.sgbm(l, r, **prm)) == 0, prm
+
+
+def test_pipeline_batch_and_streaming_match_single_calls(svgpu, oracle):
+    """svgpu_pipeline_batch / svgpu_pipeline_enqueue_batch (the folder and livecam loops, static-image-main.cpp:107-127,
+    livecam-main.cpp:70-106, n frames per call): every output of every frame equals the single-frame svgpu_pipeline call, which
+    the bottle test pins to cv2 — host buffers in two chunks, device tensors, and three overlapping streamed batches."""
+    import torch
+    g = golden("bottle")
+    size = (640, 480)
+    ml = oracle.init_undistort_rectify_map(g["cal_Kl"], g["cal_Dl"], g["rect_Rl"], g["rect_Pl"], size)
+    mr = oracle.init_undistort_rectify_map(g["cal_Kr"], g["cal_Dr"], g["rect_Rr"], g["rect_Pr"], size)
+    a, b = np.ascontiguousarray(g["scaled_left"]), np.ascontiguousarray(g["scaled_right"])
+    L = np.stack([a, a[::-1].copy(), np.roll(a, 40, axis=1), a])
+    R = np.stack([b, b[::-1].copy(), np.roll(b, 40, axis=1), np.roll(b, 3, axis=0)])
+    ALL = (svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM | svgpu.STAGE_POSTFILTER | svgpu.STAGE_REPROJECT | svgpu.STAGE_DEPTH)
+    keys = ("left_rect", "right_rect", "disp", "xyz", "depth")
+    with svgpu.Context(*size) as ctx:
+        ctx.set_rectify_maps(0, *ml)
+        ctx.set_rectify_maps(1, *mr)
+        ctx.set_Q(g["Q"])
+        ctx.set_depth_consts(float(g["baseline"]), float(g["focal"]))
+        ctx.set_sgbm(**svgpu.REFERENCE_SGBM)
+        single = [ctx.pipeline(L[i], R[i], ALL, want_rect=True, want_xyz=True, want_depth=True) for i in range(4)]
+        assert nmismatch(single[0]["disp"], g["disp_post"]) == 0
+
+        def check(out, idx, tag):
+            for q, i in enumerate(idx):
+                for k in keys:
+                    got = out[k][q].cpu().numpy() if hasattr(out[k], "cpu") else out[k][q]
+                    assert nmismatch(got.view(np.uint8), np.ascontiguousarray(single[i][k]).view(np.uint8)) == 0, (tag, i, k)
+
+        ctx.reserve(3)  # 4 frames = two chunks (3 + 1)
+        check(ctx.pipeline_batch(L, R, ALL, want_rect=True, want_xyz=True, want_depth=True), range(4), "host")
+        tl, tr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+        out = ctx.pipeline_batch(tl, tr, ALL, want_rect=True, want_xyz=True, want_depth=True)
+        torch.cuda.synchronize()
+        check(out, range(4), "device")
+        # SGBM on 8UC3 frames without the pre-filter chain, batched == single
+        raw1 = ctx.pipeline(L[1], R[1], svgpu.STAGE_REMAP | svgpu.STAGE_SGBM)["disp"]
+        rawb = ctx.pipeline_batch(L[:2], R[:2], svgpu.STAGE_REMAP | svgpu.STAGE_SGBM)["disp"]
+        assert nmismatch(rawb[1], raw1) == 0
+        # streaming: three batches in flight, results read after sync()
+        ctx.use_own_stream()
+        order = [(0, 1, 2), (3, 0), (2, 3, 1)]
+        ins = [(np.ascontiguousarray(L[list(o)]), np.ascontiguousarray(R[list(o)])) for o in order]
+        outs = []
+        for (li, ri), o in zip(ins, order):
+            n = len(o)
+            pre = dict(disp=np.zeros((n, 480, 640), np.int16), xyz=np.zeros((n, 480, 640, 3), np.float32), depth=np.zeros((n, 480, 640), np.float32),
+                       left_rect=np.zeros((n, 480, 640, 3), np.uint8), right_rect=np.zeros((n, 480, 640, 3), np.uint8))
+            outs.append(ctx.pipeline_enqueue(li, ri, ALL, pre, want_rect=True, want_xyz=True, want_depth=True))
+        ctx.sync()
+        for o, res in zip(order, outs):
+            check(res, o, "stream")
