@@ -19,6 +19,8 @@
 #include <utility>
 #include <vector>
 
+#include <stereo-vision-gpu/StereoCameraInfo.hpp>
+
 struct svgpu_ctx;
 
 namespace stereo_vision {
@@ -82,15 +84,6 @@ namespace stereo_vision {
     float focal_length = 0.0f;                        ///< camera_matrix_left(0,0)
   };
 
-  /// StereoCameraInfo.hpp:15-45 without cv::Mat: what the calibration YAML holds and rectification needs (row-major).
-  struct StereoCameraInfo {
-    int width = 0, height = 0;                        ///< image_size
-    std::array<double, 9> camera_matrix_left{}, camera_matrix_right{};
-    std::array<double, 5> dist_coeffs_left{}, dist_coeffs_right{};   ///< k1 k2 p1 p2 k3
-    std::array<double, 9> R{};
-    std::array<double, 3> T{};
-  };
-
   class StereoVision {
   public:
     struct Settings {
@@ -104,7 +97,9 @@ namespace stereo_vision {
       std::optional<StereoCameraInfo> stereo_camera_info;
       /// ... or the products of those calls, computed elsewhere (e.g. by OpenCV in the reference's constructor).
       Rectification rectification;
-      Algorithm algorithm = Algorithm::kSGBM;         ///< only kSGBM has a GPU path
+      /// lib.hpp:80 — same default as the reference.  Only kSGBM (the dense path, src/lib.cpp:67-69) has a GPU implementation;
+      /// kMatchTemplate and kORB (src/lib.cpp:61-66, per-point CPU heuristics outside the hot path) yield kInvalidSettings.
+      Algorithm algorithm = Algorithm::kMatchTemplate;
       bool show_debug_info = false;
       int device = 0;                                 ///< CUDA device of this instance
     };
@@ -124,7 +119,8 @@ namespace stereo_vision {
                                                std::pair<Point, Point> const& search_points) const
         -> std::expected<AnalysisResult, AnalysisError>;
 
-    [[nodiscard]] Settings const& settings() const { return this->settings_; }
+    /// lib.hpp:111-112 — returns a copy, like the reference.
+    [[nodiscard]] Settings settings() const { return this->settings_; }
 
   private:
     Settings settings_;

@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
   int const W = hdr[0], H = hdr[1];
   std::size_t const n = static_cast<std::size_t>(W) * H;
   StereoVision::Settings s;
+  s.algorithm = StereoVision::Settings::Algorithm::kSGBM;  // the reference's default is kMatchTemplate (lib.hpp:80)
   auto& r = s.rectification;
   r.width = W; r.height = H;
   std::vector<double> q;

@@ -387,9 +387,38 @@ def save_big(path):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def save_calibration_yml(path):
+    """A calibration file as the reference's calibration application writes it (StereoCameraInfo.hpp:51-65: cv::FileStorage,
+    node `calibration`), from seeded values with awkward decimals; the facade's reader / writer is pinned to it byte for byte."""
+    rng = np.random.default_rng(2026)
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+    fs.startWriteStruct("calibration", cv2.FileNode_MAP)
+    fs.write("file_version", 1)
+    fs.startWriteStruct("image_size", cv2.FileNode_SEQ | cv2.FileNode_FLOW)
+    fs.write("", 1920)
+    fs.write("", 1080)
+    fs.endWriteStruct()
+    K = lambda: np.array([[1400 + rng.normal() * 30, 0, 960 + rng.normal() * 9], [0, 1400 + rng.normal() * 30, 540 + rng.normal() * 9], [0, 0, 1]])  # noqa: E731
+    fs.write("camera_matrix_left", K())
+    fs.write("camera_matrix_right", K())
+    fs.write("dist_coeffs_left", (rng.normal(size=(1, 5)) * [0.3, 0.1, 1e-3, 1e-3, 1e-2]))
+    fs.write("dist_coeffs_right", (rng.normal(size=(1, 5)) * [0.3, 0.1, 1e-3, 1e-3, 1e-2]))
+    R, _ = cv2.Rodrigues(rng.normal(size=3) * 0.03)
+    fs.write("R", R)
+    fs.write("T", np.array([[-120.5 + rng.normal()], [rng.normal()], [rng.normal() * 1e-3]]))
+    fs.write("E", rng.normal(size=(3, 3)) * 50)
+    fs.write("F", rng.normal(size=(3, 3)) * 1e-7)
+    fs.write("reprojection_error", float(abs(rng.normal()) * 0.3))
+    fs.endWriteStruct()
+    fs.release()
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     jobs = dict(big_sha=save_big, sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))
+    if not only or "calibration_cv2" in only:
+        save_calibration_yml(os.path.join(HERE, "calibration_cv2.yml"))
