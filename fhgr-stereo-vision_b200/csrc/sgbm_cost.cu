@@ -24,12 +24,6 @@
 #include "common.cuh"
 #include "sgbm_device.cuh"
 
-#ifndef SV_COST_COLS
-#define SV_COST_COLS 1
-#endif
-#ifndef SV_COST_MINB
-#define SV_COST_MINB SV_COST_COLS   // CTAs per SM the register allocation is bounded for (threads per CTA = 512 / COLS)
-#endif
 
 namespace svgpu {
 
@@ -39,11 +33,13 @@ struct CostGeom {
   int NJ;      // right-image records per row: reversed positions 0 .. NC + D - 10
   int ng;      // groups of 16 disparities
   int rowU4;   // uint4 per (row, half-group) line of the Vs buffer: NC + 1 (padding against bank conflicts)
-  size_t offL, offR, offV, total;  // byte offsets in dynamic shared memory
+  size_t offL, offR, offV, offRing, total;  // byte offsets in dynamic shared memory
 };
+
 // CH = operand planes per image row: 2 (gradient, intensity) per colour channel
-template <int NC, int RB, int CH>
-__host__ __device__ inline CostGeom cost_geom(int D) {
+// SRING: the pixel costs of the last 2r+1 rows live in shared memory (thread-private slots) instead of registers
+template <int NC, int RB, int CH, bool SRING>
+__host__ __device__ inline CostGeom cost_geom(int D, int R) {
   CostGeom g;
   g.ng = D / kDPL;
   g.NJ = (NC + D - 9 + 1) & ~1;   // even: the records of even and odd positions form two planes when a thread owns two columns
@@ -51,7 +47,8 @@ __host__ __device__ inline CostGeom cost_geom(int D) {
   g.offL = 0;                                        // [2 rows][CH planes][NC] uint4
   g.offR = g.offL + (size_t)2 * CH * NC * 16;        // [2 rows][CH planes][NJ] uint4
   g.offV = g.offR + (size_t)2 * CH * g.NJ * 16;      // [RB][ng*2][NC+1] uint4
-  g.total = g.offV + (size_t)RB * g.ng * 2 * g.rowU4 * 16;
+  g.offRing = g.offV + (size_t)RB * g.ng * 2 * g.rowU4 * 16;   // [2R+1][words per cell block][NC x ng threads-columns] uint4
+  g.total = g.offRing + (SRING ? (size_t)(2 * R + 1) * (CH == 2 ? 1 : 2) * NC * g.ng * 16 : 0);
   return g;
 }
 
@@ -64,15 +61,16 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
 
 // COLS neighbouring columns per thread: 8 of the 9 right-image records of two neighbouring columns are the same,
 // so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
-template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
-__global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1 : SV_COST_MINB) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
                                                                 uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4,
                                                                 int planeRows, int rowsOut) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
   extern __shared__ uint4 smemU4[];
   const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
-  const CostGeom G = cost_geom<NC, RB, CH>(D);
+  const CostGeom G = cost_geom<NC, RB, CH, SRING>(D, R);
   uint4* sL = smemU4 + G.offL / 16;
+  uint4* sRing = smemU4 + G.offRing / 16;
   uint4* sR = smemU4 + G.offR / 16;
   uint4* sV = smemU4 + G.offV / 16;
   const int NJ = G.NJ, ng = G.ng;
@@ -162,15 +160,23 @@ __global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1
   // the pixel costs of the last 2r+1 rows: one byte per cost for a single channel (<= 2*63 + 63), 16 bits for three
   constexpr bool RING8 = CH == 2;
   constexpr int RINGW = RING8 ? kNR / 2 : kNR;
-  uint32_t Vs[COLS][kNR], pix[COLS][kNR], ring[NRING][COLS][RINGW];
+  constexpr int RINGU4 = RINGW / 4;              // uint4 per (slot, column) of the shared-memory ring
+  uint32_t Vs[COLS][kNR], pix[COLS][kNR], ring[SRING ? 1 : NRING][COLS][RINGW];
+  // shared-memory ring: slot k of column m of this thread = RINGU4 words at sRing[((k * COLS + m) * RINGU4 + w) * nthr + tid]
 #pragma unroll
   for (int m = 0; m < COLS; m++) {
 #pragma unroll
     for (int i = 0; i < kNR; i++) Vs[m][i] = pix[m][i] = 0;
 #pragma unroll
-    for (int k = 0; k < NRING; k++)
+    for (int k = 0; k < NRING; k++) {
+      if constexpr (SRING) {
 #pragma unroll
-      for (int i = 0; i < RINGW; i++) ring[k][m][i] = 0;
+        for (int w = 0; w < RINGU4; w++) sRing[((k * COLS + m) * RINGU4 + w) * nthr + tid] = make_uint4(0, 0, 0, 0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RINGW; i++) ring[k][m][i] = 0;
+      }
+    }
   }
 
   const int vbeg = yb - R, vend = ye - 1 + R;  // virtual rows whose pixel costs enter the band's sums
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1
   int computed = -1;                            // image row whose pixel costs are in `pix`
 
   for (int v0 = vbeg; v0 <= vend; v0 += NRING) {
-#pragma unroll
+#pragma unroll(SRING ? 1 : NRING)
     for (int k = 0; k < NRING; k++) {
       const int v = v0 + k;
       if (v > vend) break;
@@ -222,20 +228,34 @@ __global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1
       const int y = v - R;  // output row completed by this virtual row
 #pragma unroll
       for (int m = 0; m < COLS; m++) {
+        constexpr int KR = SRING ? 0 : 1;   // register ring: slot k; shared-memory ring: one staging copy
+        if constexpr (SRING) {
+#pragma unroll
+          for (int w = 0; w < RINGU4; w++) {
+            const uint4 o = sRing[((k * COLS + m) * RINGU4 + w) * nthr + tid];
+            ring[0][m][4 * w] = o.x; ring[0][m][4 * w + 1] = o.y; ring[0][m][4 * w + 2] = o.z; ring[0][m][4 * w + 3] = o.w;
+          }
+        }
         if constexpr (RING8) {
 #pragma unroll
           for (int i = 0; i < kNR / 2; i++) {
-            const uint32_t old = ring[k][m][i];
+            const uint32_t old = ring[k * KR][m][i];
             Vs[m][2 * i] += pix[m][2 * i] - __byte_perm(old, 0, 0x4140);
             Vs[m][2 * i + 1] += pix[m][2 * i + 1] - __byte_perm(old, 0, 0x4342);
-            ring[k][m][i] = __byte_perm(pix[m][2 * i], pix[m][2 * i + 1], 0x6420);
+            ring[k * KR][m][i] = __byte_perm(pix[m][2 * i], pix[m][2 * i + 1], 0x6420);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < kNR; i++) {
-            Vs[m][i] += pix[m][i] - ring[k][m][i];
-            ring[k][m][i] = pix[m][i];
+            Vs[m][i] += pix[m][i] - ring[k * KR][m][i];
+            ring[k * KR][m][i] = pix[m][i];
           }
+        }
+        if constexpr (SRING) {
+#pragma unroll
+          for (int w = 0; w < RINGU4; w++)
+            sRing[((k * COLS + m) * RINGU4 + w) * nthr + tid] =
+                make_uint4(ring[0][m][4 * w], ring[0][m][4 * w + 1], ring[0][m][4 * w + 2], ring[0][m][4 * w + 3]);
         }
         if (y >= yb) {
           uint4* dst = sV + ((size_t)((y - yb) % RB) * ng * 2 + g * 2) * G.rowU4 + vpos(c0 + m);
@@ -274,10 +294,12 @@ __global__ void __launch_bounds__((NC == 128 ? 1024 : 512) / COLS, COLS == 1 ? 1
   }
 }
 
-template <int R, int NC, int COLS, int RB, int ITEMS, int CH>
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT>
 cudaError_t launch_cost(const SgbmCfg& cfg, const CostView& v, int nframes, cudaStream_t st) {
-  const CostGeom G = cost_geom<NC, RB, CH>(cfg.D);
-  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH>;
+  const CostGeom G = cost_geom<NC, RB, CH, SRING>(cfg.D, R);
+  const int threads = (NC / COLS) * (cfg.D / kDPL);
+  if (G.total > 227 * 1024 || threads > MAXT) return cudaErrorInvalidConfiguration;   // the callers pick configurations that fit
+  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH, SRING, MAXT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
@@ -297,20 +319,33 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const CostView& v, int nframes, cuda
     }
   }
   dim3 grid(tiles, bands, nframes);
-  k<<<grid, (NC / COLS) * (cfg.D / kDPL), G.total, st>>>((const uint2*)v.planesL, (const uint2*)v.planesR, (uint4*)v.C, cfg, rowsPerBand,
-                                                         v.frameCells / 8, v.planeRows, v.rowsOut);
+  k<<<grid, threads, G.total, st>>>((const uint2*)v.planesL, (const uint2*)v.planesR, (uint4*)v.C, cfg, rowsPerBand, v.frameCells / 8, v.planeRows,
+                                    v.rowsOut);
   return cudaGetLastError();
 }
 
+// general kernel: one column per thread, the row ring in registers, any block radius / channel count
 template <int NC, int COLS, int RB, int ITEMS, int CH = 2>
 cudaError_t launch_cost_r(const SgbmCfg& cfg, const CostView& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
-    case 3: return launch_cost<3, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
-    case 4: return launch_cost<4, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
-    default: return launch_cost<5, NC, COLS, RB, ITEMS, CH>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+    case 3: return launch_cost<3, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+    case 4: return launch_cost<4, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+    default: return launch_cost<5, NC, COLS, RB, ITEMS, CH, false, 512>(cfg, sc, nframes, st);
+  }
+}
+// throughput kernel for single-channel input with blockSize <= 7 and 64..256 disparities: two neighbouring columns per thread
+// (9 instead of 16 right-image records per 16 pixel costs), the row ring in shared memory (no register spills at 128
+// registers), horizontal phase every two rows
+template <int NC, int ITEMS>
+cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes, cudaStream_t st) {
+  switch (cfg.r) {
+    case 0: return launch_cost<0, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
+    default: return launch_cost<3, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
   }
 }
 
@@ -325,25 +360,19 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes
     if (cfg.D >= 48) return launch_cost_r<64, 1, 8, 6, 6>(cfg, sc, nframes, st);
     return launch_cost_r<64, 1, 8, 15, 6>(cfg, sc, nframes, st);
   }
-#if SV_COST_COLS == 2
-  // two columns per thread, 32 column pairs x D/16 groups <= 256 threads, two CTAs per SM
-  if (cfg.D > 128) return launch_cost_r<32, 2, 4, 3>(cfg, sc, nframes, st);   // 16 pairs x <= 16 groups
-#ifndef SV_COST_NC
-#define SV_COST_NC 64
-#endif
-#ifndef SV_COST_RB
-#define SV_COST_RB 4
-#endif
-  if (cfg.D == 128) return launch_cost_r<SV_COST_NC, 2, SV_COST_RB, 2>(cfg, sc, nframes, st);
-  if (cfg.D >= 64) return launch_cost_r<64, 2, 4, 3>(cfg, sc, nframes, st);
-  return launch_cost_r<64, 2, 4, 9>(cfg, sc, nframes, st);
-#else
+  if (cfg.r <= 3 && cfg.D >= 64) {
+    // threads = NC / 2 x D / 16 <= 512; records staged per thread and row = 2 (NC + NJ) / threads
+    const int D = cfg.D;
+    if (D > 128) return launch_cost_pair<64, 2>(cfg, sc, nframes, st);
+    if (D >= 96) return launch_cost_pair<128, 2>(cfg, sc, nframes, st);
+    if (D > 64) return launch_cost_pair<128, 3>(cfg, sc, nframes, st);
+    return launch_cost_pair<256, 3>(cfg, sc, nframes, st);
+  }
   // one column per thread: 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
   if (cfg.D > 128) return launch_cost_r<32, 1, 8, 2>(cfg, sc, nframes, st);
   if (cfg.D == 128) return launch_cost_r<64, 1, 8, 1>(cfg, sc, nframes, st);
   if (cfg.D >= 48) return launch_cost_r<64, 1, 8, 2>(cfg, sc, nframes, st);
   return launch_cost_r<64, 1, 8, 5>(cfg, sc, nframes, st);
-#endif
 }
 
 }  // namespace svgpu

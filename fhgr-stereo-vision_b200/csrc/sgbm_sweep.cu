@@ -72,6 +72,9 @@ namespace {
 #ifndef SV_SWEEP_PIXFENCE
 #define SV_SWEEP_PIXFENCE 0  // 1: compiler-level memory fence between the pixels of a chunk (keeps their loads / stores from being batched)
 #endif
+#ifndef SV_SWEEP_LDASM
+#define SV_SWEEP_LDASM 0     // 1: operand prefetch through volatile inline PTX (keeps the loads where the source puts them)
+#endif
 #ifndef SV_SWEEP_FAKE
 #define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
 #endif
@@ -185,6 +188,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, int parity) {
   return ok != 0;
 }
 
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+#if SV_SWEEP_LDASM
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldcs(p);
+#endif
+}
 __device__ __forceinline__ unsigned long long now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -438,6 +450,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       // predicated.  The test is warp-uniform arithmetic on T, so the warp takes one of two copies of the chunk code.
       auto phaseB = [&](auto interiorTag) {
       constexpr bool IN = decltype(interiorTag)::value;
+      // which parts of the chunk code the interior copy simplifies (SV_SWEEP_INTERIOR is a bit mask: 1 = enabled; the bits
+      // 2 / 4 / 8 / 16 keep the general form of the operand loads / the 'outside' flags / the stores / the row flags)
+      constexpr bool IN_LD = IN && !(SV_SWEEP_INTERIOR & 2), IN_OUT = IN && !(SV_SWEEP_INTERIOR & 4), IN_ST = IN && !(SV_SWEEP_INTERIOR & 8),
+                     IN_ROW = IN && !(SV_SWEEP_INTERIOR & 16);
       const int yp = a.flip ? H - 1 - r : r;
       const int ypn = a.flip ? yp - 1 : yp + 1;                     // next row of this worker
       // volume offsets of the chunk's first pixel in this row and of the first pixel fetched for the next row; the chunk
@@ -445,13 +461,13 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       const int stepU4 = a.flip ? -a.pixU4 : a.pixU4;
       const unsigned offRow0 = (unsigned)yp * a.rowU4 + (unsigned)(a.flip ? W1 - 1 - xl : xl) * (unsigned)a.pixU4;
       const unsigned offNext0 = (unsigned)ypn * a.rowU4 + (unsigned)(a.flip ? W1 - xl : xl - 1) * (unsigned)a.pixU4;
-      uint2* selRow = SECOND ? a.sel + ((size_t)frame * H + ((IN || act) ? yp : 0)) * W1 : nullptr;  // selection output row of this step
-      const bool actn = IN || ((r + 1) >= y0 && (r + 1) <= y1);
-      const bool top = !IN && r == 0;
+      uint2* selRow = SECOND ? a.sel + ((size_t)frame * H + ((IN_ROW || act) ? yp : 0)) * W1 : nullptr;  // selection output row of this step
+      const bool actn = IN_LD || ((r + 1) >= y0 && (r + 1) <= y1);
+      const bool top = !IN_OUT && r == 0;
       // export target of this chunk: the ring of the right neighbour, or (no neighbour / inactive row / neighbour in
       // another CTA) a private entry that the last warp copies to global memory after the chunk
-      const bool toRing = (j < RW - 1) || (hasRight && (IN || act) && !rightGlobal);
-      const bool expGlobal = (j == RW - 1) && rightGlobal && (IN || act);
+      const bool toRing = (j < RW - 1) || (hasRight && (IN_ROW || act) && !rightGlobal);
+      const bool expGlobal = (j == RW - 1) && rightGlobal && (IN_ROW || act);
       uint4* eOut = (toRing ? outRing + (r & outMask) * ENT : wbase + G::OFF_XOUT) + gl;
       uint32_t mDLprev = 0;
       uint4 eMins = make_uint4(0, 0, 0, 0);
@@ -459,8 +475,9 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       for (int i = 0; i < kK; i++) {
         if (SV_SWEEP_PIXFENCE && i > 0) asm volatile("" ::: "memory");
         const int x = xl + i;
-        const bool on = IN || (act && (unsigned)x < (unsigned)W1);
-        const bool xFirst = !IN && x == 0, xLast = !IN && x == W1 - 1;
+        const bool on = IN_ST || (act && (unsigned)x < (unsigned)W1);   // stores, selection output
+        const bool onP = IN_OUT || (act && (unsigned)x < (unsigned)W1);  // the pixel takes part in the paths
+        const bool xFirst = !IN_OUT && x == 0, xLast = !IN_OUT && x == W1 - 1;
         const int xp = a.flip ? W1 - 1 - x : x;
         // ---- operands of this pixel were loaded one chunk ago; fetch those of the pixel below-left now
         uint32_t c[kNR], sin[kNR];
@@ -471,22 +488,22 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         }
         {
           const int xn = x - 1;
-          const bool ld = IN || (actn && (unsigned)xn < (unsigned)W1);
+          const bool ld = IN_LD || (actn && (unsigned)xn < (unsigned)W1);
 #if SV_SWEEP_UNCOND
           // always load (from a safe address when there is nothing to fetch) so that the data lands in cb/sb directly
           const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
 #pragma unroll
           for (int h = 0; h < NV; h++) {
-            cb[i][h] = __ldcs(Cf + off + h);
-            if (SECOND) sb[i][h] = __ldcs(Sf + off + h);
+            cb[i][h] = ld_stream(Cf + off + h);
+            if (SECOND) sb[i][h] = ld_stream(Sf + off + h);
           }
 #else
           if (ld) {
             const unsigned off = offNext0 + (unsigned)(i * stepU4);
 #pragma unroll
             for (int h = 0; h < NV; h++) {
-              cb[i][h] = __ldcs(Cf + off + h);
-              if (SECOND) sb[i][h] = __ldcs(Sf + off + h);
+              cb[i][h] = ld_stream(Cf + off + h);
+              if (SECOND) sb[i][h] = ld_stream(Sf + off + h);
             }
           }
 #endif
@@ -510,47 +527,47 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         uint32_t mV = mVd1, mDL = mDLd2;
         if (HAS_DR) {
           constexpr bool HV = SV_SWEEP_MINPAIR != 0;
-          const uint32_t lDR = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(DRin, mDR, !on || top || xLast, c, kc, gl, lastLane, active, lane);
-          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+          const uint32_t lDR = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(DRin, mDR, !onP || top || xLast, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !onP || xFirst, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP, HV>(lH, lDR, lane, mH, mDR);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + DRin[q] : __viaddmin_u16x2(Hs[q], DRin[q], kMax2);
-          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 1), HV>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
-          const uint32_t lDL = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 2), HV>(DLd2, mDL, !on || top || xFirst, c, kc, gl, lastLane, active, lane);
+          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 1), HV>(Vd1, mV, !onP || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lDL = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 2), HV>(DLd2, mDL, !onP || top || xFirst, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP, HV>(lV, lDL, lane, mV, mDL);
 #pragma unroll
           for (int q = 0; q < kNR; q++)
             sum[q] = SMALL ? sum[q] + Vd1[q] + DLd2[q] : __viaddmin_u16x2(__viaddmin_u16x2(sum[q], Vd1[q], kMax2), DLd2[q], kMax2);
         } else if (HAS_V) {
           constexpr bool HV = SV_SWEEP_MINPAIR != 0;
-          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
-          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+          const uint32_t lV = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 0), HV>(Vd1, mV, !onP || top, c, kc, gl, lastLane, active, lane);
+          const uint32_t lH = sweep_path_core<LPP, (SV_SWEEP_FMAADD > 3), HV>(Hs, mH, !onP || xFirst, c, kc, gl, lastLane, active, lane);
           group_min2_u16<LPP, HV>(lH, lV, lane, mH, mV);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = SMALL ? Hs[q] + Vd1[q] : __viaddmin_u16x2(Hs[q], Vd1[q], kMax2);
         } else {
-          sweep_path_step<LPP>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(Hs, mH, !onP || xFirst, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
         }
 #else
-        sweep_path_step<LPP>(Hs, mH, !on || xFirst, c, kc, gl, lastLane, active, lane);
+        sweep_path_step<LPP>(Hs, mH, !onP || xFirst, c, kc, gl, lastLane, active, lane);
         uint32_t sum[kNR];
 #pragma unroll
         for (int q = 0; q < kNR; q++) sum[q] = Hs[q];
         uint32_t mV = mVd1, mDL = mDLd2;
         if (HAS_V) {
-          sweep_path_step<LPP>(Vd1, mV, !on || top, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(Vd1, mV, !onP || top, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], Vd1[q], kMax2);
         }
         if (HAS_DL) {
-          sweep_path_step<LPP>(DLd2, mDL, !on || top || xFirst, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(DLd2, mDL, !onP || top || xFirst, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DLd2[q], kMax2);
         }
         if (HAS_DR) {
-          sweep_path_step<LPP>(DRin, mDR, !on || top || xLast, c, kc, gl, lastLane, active, lane);
+          sweep_path_step<LPP>(DRin, mDR, !onP || top || xLast, c, kc, gl, lastLane, active, lane);
 #pragma unroll
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DRin[q], kMax2);
         }
@@ -628,8 +645,13 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       {
         const int xw = sFirst * kK - T;  // leftmost column of worker 0's chunk; worker j starts (kK + 1) j columns further right
         const bool interior = T >= RW && T <= H - 2 && xw >= 1 && xw + (kK + 1) * (RW - 1) + kK - 1 <= W1 - 2;
-        if (SV_SWEEP_INTERIOR && interior) phaseB(std::true_type{});
-        else phaseB(std::false_type{});
+        if constexpr ((SV_SWEEP_INTERIOR & 1) != 0) {
+          if (interior) phaseB(std::true_type{});
+          else phaseB(std::false_type{});
+        } else {
+          (void)interior;
+          phaseB(std::false_type{});
+        }
       }
 }
 #if SV_SWEEP_PROF

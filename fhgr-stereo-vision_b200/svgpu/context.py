@@ -230,10 +230,12 @@ class Context:
         self._keep = getattr(self, "_keep", [])[-8:] + [(left, right, out)]
         self._check(self._lib.svgpu_sgbm_enqueue_batch(self._h, n, self._ptr(left), self._ptr(right), self._ptr(out)))
 
-    def bm(self, left, right):
+    def bm(self, left, right, out=None):
         """cv::StereoBM::compute — BASELINE config 2."""
         left, right = self._pair(left, right)
-        disp = self._out_like(left, (self.height, self.width), np.int16)
+        disp = out if out is not None else self._out_like(left, (self.height, self.width), np.int16)
+        if out is not None and (_is_tensor(out) != _is_tensor(left) or tuple(out.shape) != (self.height, self.width)):
+            raise ValueError("out must be [H][W] int16 in the same memory as the inputs")
         self._check(self._lib.svgpu_bm_compute(self._h, self._ptr(left), self._stride(left), self._ptr(right),
                                                self._stride(right), self._ptr(disp), self._stride(disp),
                                                self._mem(left, right)))

@@ -26,5 +26,5 @@ for k, rs in agg.items():
     bw = (rd + wr) / (t * 1e-6) / 1e9 if t else 0
     print(f"| {k[:60]} | {len(rs)} | {t:.1f} | {rd/1e6:.1f} | {wr/1e6:.1f} | {bw:.0f} | {bw/peak:.2f} | "
           f"{g(r,'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'):.0f} | {g(r,'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'):.0f} | "
-          f"{g(r,'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'):.0f} | {g(r,'sm__issue_active.avg.pct_of_peak_sustained_active'):.0f} | "
+          f"{g(r,'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'):.0f} | {g(r,'sm__inst_issued.avg.pct_of_peak_sustained_active'):.0f} | "
           f"{g(r,'launch__registers_per_thread'):.0f} | {g(r,'sm__warps_active.avg.per_cycle_active')/4:.1f} |")
