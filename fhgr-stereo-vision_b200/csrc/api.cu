@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -191,8 +192,9 @@ int d2h_2d(svgpu_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitc
   return SV_OK;
 }
 
+// planesReady: the operand planes of the n pairs were written into the scratch by the fused front kernel (dl / dr unused)
 int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const uint8_t* dr, size_t rs, size_t rf,
-             int16_t* dd, size_t ds, size_t df, int cn = 1) {
+             int16_t* dd, size_t ds, size_t df, int cn = 1, bool planesReady = false) {
   // 8UC3 input: the pixel cost is the sum over the three channels, so the 16-bit headroom shrinks accordingly
   if (cn == 3 && (long long)(2 * c->cfg.r + 1) * (2 * c->cfg.r + 1) * 3 * (2 * c->cfg.ftzero + 63) + c->cfg.P2 > 32767)
     return fail(c, SV_INVALID_SETTINGS, "3 * blockSize^2*(2*ftzero+63) + P2 exceeds the 16-bit cost range for 3-channel input");
@@ -203,6 +205,7 @@ int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const
     return fail(c, SV_INVALID_SETTINGS, "image too narrow for minDisparity + numDisparities and blockSize");
   int rc = ensure_scratch(c, std::max(n, c->maxBatch), cn);
   if (rc) return rc;
+  if (planesReady) dl = dr = nullptr;
   cudaError_t e = sgbm_forward(c->cfg, c->sc, n, dl, ls, lf, dr, rs, rf, dd, ds, df, c->st, &c->stats,
                                c->timing ? c->ev : nullptr, c->debugS ? 1 : 0, cn);
   if (e != cudaSuccess) return cuda_fail(c, e, "sgbm_forward");
@@ -229,6 +232,7 @@ struct PipeDev {
   int cn;
   uint8_t *rectL, *rectR;        // remap output (null: context scratch); filled in with what was used
   size_t rectS, rectF;
+  bool wantRect;                 // the caller reads the rectified images after the call (else they may never be materialised)
   int16_t* disp;                 // in (without the SGBM stage) / out
   size_t dS, dF;
   float* xyz;                    // null: skipped
@@ -264,6 +268,28 @@ int pipeline_device(svgpu_ctx* c, int n, PipeDev& p, unsigned stages) {
   int rc;
   const uint8_t *curL = p.left, *curR = p.right;
   size_t curLs = p.ls, curRs = p.rs, curLf = p.lf, curRf = p.rf;
+  // Raw BGR frames through remap + blur / gray / sharpen + SGBM: one kernel produces the operand planes of the cost kernel
+  // (front_fused.cu); rectified pixels, blurred rows and gray images never go through HBM.  SVGPU_UNFUSED=1 (read once) keeps
+  // the stage-by-stage kernels, which the parity tests compare against.
+  static const bool unfused = [] { const char* e = std::getenv("SVGPU_UNFUSED"); return e && e[0] == '1'; }();
+  const unsigned kFront = SV_STAGE_REMAP | SV_STAGE_PREFILTER | SV_STAGE_SGBM;
+  const bool fused = !unfused && (stages & kFront) == kFront && cn == 3 && c->cfg.W1 > 0 &&
+                     (c->cfg.mode == SV_MODE_HH4 || c->W - (c->cfg.minD + c->cfg.D) > c->cfg.r);
+  if (fused) {
+    if (p.wantRect && (!p.rectL || !p.rectR)) {
+      rc = ensure(c, c->stRectL, W * H * cn * n); if (rc) return rc;
+      rc = ensure(c, c->stRectR, W * H * cn * n); if (rc) return rc;
+      p.rectL = (uint8_t*)c->stRectL.p; p.rectR = (uint8_t*)c->stRectR.p; p.rectS = W * cn; p.rectF = W * H * cn;
+    }
+    rc = ensure_scratch(c, std::max(n, c->maxBatch), 1); if (rc) return rc;
+    const int16_t* m1[2] = {c->map1[0], c->map1[1]};
+    const uint16_t* m2[2] = {c->map2[0], c->map2[1]};
+    CU(c, launch_front_fused(curL, curLs, curLf, curR, curRs, curRf, m1, m2, p.wantRect ? p.rectL : nullptr, p.wantRect ? p.rectR : nullptr, p.rectS,
+                             p.rectF, c->sc.planesL, c->sc.planesR, c->W, c->H, c->cfg.Wp, c->cfg.ftzero, n, c->st));
+    c->stats.launches++;
+    rc = run_sgbm(c, n, nullptr, 0, 0, nullptr, 0, 0, p.disp, p.dS, p.dF, 1, true); if (rc) return rc;
+    stages &= ~kFront;
+  }
   if (stages & SV_STAGE_REMAP) {  // src/lib.cpp:87-94
     if (!p.rectL || !p.rectR) {
       rc = ensure(c, c->stRectL, W * H * cn * n); if (rc) return rc;
@@ -304,7 +330,7 @@ int pipeline_device(svgpu_ctx* c, int n, PipeDev& p, unsigned stages) {
       CU(c, launch_filter_speckles(dd, p.dS, c->W, c->H, 0, 150, 32, (int*)c->stLabels.p, (int*)c->stSizes.p, nullptr, c->st, &nl));
       CU(c, launch_morph_close5(dd, p.dS, (int16_t*)c->stLabels.p, (int16_t*)c->stDisp2.p, W * 2, c->W, c->H, c->st));
       CU(c, cudaMemcpy2DAsync(dd, p.dS, c->stDisp2.p, W * 2, W * 2, H, cudaMemcpyDeviceToDevice, c->st));
-      c->stats.launches += nl + 2;
+      c->stats.launches += nl + 1;
     }
   }
   if ((stages & SV_STAGE_REPROJECT) && p.xyz) {  // src/lib.cpp:152-156
@@ -742,7 +768,7 @@ SVGPU_API int svgpu_morph_close5(svgpu_ctx* c, const int16_t* src, size_t ss, in
     s = (int16_t*)c->stDisp.p; d = (int16_t*)c->stDisp2.p; sss = dds = W * 2;
   }
   CU(c, launch_morph_close5(s, sss, (int16_t*)c->stLabels.p, d, dds, c->W, c->H, c->st));
-  c->stats.launches += 2;
+  c->stats.launches += 1;
   if (mem == SV_MEM_HOST) {
     rc = d2h_2d(c, dst, dstride, d, dds, W * 2, (int)H); if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->st));
@@ -851,6 +877,7 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
     p.left = (uint8_t*)c->stLeft.p; p.right = (uint8_t*)c->stRight.p; p.ls = p.rs = W * cn;
   }
   if (!host && io->left_rect && io->right_rect) { p.rectL = io->left_rect; p.rectR = io->right_rect; p.rectS = io->rect_stride; }
+  p.wantRect = io->left_rect || io->right_rect;
   p.disp = io->disp; p.dS = io->disp_stride;
   if (host || !p.disp) {
     rc = ensure(c, c->stDisp, W * H * 2); if (rc) return rc;
@@ -903,6 +930,7 @@ SVGPU_API int svgpu_pipeline_batch(svgpu_ctx* c, int n, const svgpu_pipeline_bat
     const int m = std::min(chunk, n - f0);
     PipeDev p{};
     p.cn = cn; p.ls = p.rs = W * cn; p.lf = p.rf = img;
+    p.wantRect = wantRect;
     p.dS = W * 2; p.dF = px * 2; p.xS = W * 12; p.xF = px * 12; p.zS = W * 4; p.zF = px * 4;
     if (host) {
       CU(c, cudaMemcpyAsync(c->stLeft.p, io->left + f0 * img, img * m, cudaMemcpyHostToDevice, c->st));
@@ -963,6 +991,7 @@ SVGPU_API int svgpu_pipeline_enqueue_batch(svgpu_ctx* c, int n, const svgpu_pipe
   if (reused) CU(c, cudaStreamWaitEvent(c->st, c->evOut[s], 0));
   PipeDev p{};
   p.cn = cn; p.ls = p.rs = W * cn; p.lf = p.rf = img;
+  p.wantRect = wantRect;
   p.left = (uint8_t*)c->pipeL[s].p; p.right = (uint8_t*)c->pipeR[s].p;
   p.disp = (int16_t*)c->pipeD[s].p; p.dS = W * 2; p.dF = px * 2;
   if (wantRect) { p.rectL = (uint8_t*)c->pipeRL[s].p; p.rectR = (uint8_t*)c->pipeRR[s].p; p.rectS = W * cn; p.rectF = img; }

@@ -125,6 +125,12 @@ cudaError_t launch_prefilter_chain(const uint8_t* bgr, size_t bstride, uint16_t*
 cudaError_t launch_resize(const uint8_t* src, int sw, int sh, size_t sstride, int cn, uint8_t* dst, int dw, int dh,
                           size_t dstride, cudaStream_t st);
 
+// front_fused.cu: raw BGR frames -> (rectified images) -> blur / gray / sharpen -> SGBM operand planes, one kernel
+cudaError_t launch_front_fused(const uint8_t* left, size_t lstride, size_t lframe, const uint8_t* right, size_t rstride, size_t rframe,
+                               const int16_t* const map1[2], const uint16_t* const map2[2], uint8_t* rectL, uint8_t* rectR, size_t rectStride,
+                               size_t rectFrame, uint8_t* planesL, uint8_t* planesR, int W, int H, int Wp, int ftzero, int nframes,
+                               cudaStream_t st);
+
 // bm.cu
 size_t bm_smem_bytes(int D, int blockSize);  // dynamic shared memory k_bm_sad needs for this configuration
 cudaError_t bm_forward(const BmCfg& cfg, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,

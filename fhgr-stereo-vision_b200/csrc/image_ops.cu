@@ -158,24 +158,47 @@ __global__ void k_min_s16(const int16_t* __restrict__ disp, size_t dstride, int 
 }
 __global__ void k_set_int(int* p, int v) { *p = v; }
 
+// PPT pixels per thread: the 3 x PPT floats of a thread are contiguous (three 16-byte stores for PPT = 4)
+template <int PPT>
 __global__ void __launch_bounds__(256) k_reproject(const int16_t* __restrict__ disp, size_t dstride, float* __restrict__ xyz,
                                                    size_t xstride, int W, int H, const double* __restrict__ Q,
                                                    int handleMissing, const int* __restrict__ minDisp) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const int di = *(const int16_t*)((const uint8_t*)disp + (size_t)y * dstride + (size_t)x * 2);
-  const double d = (double)di;
-  double h[4];
+  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * PPT, y = blockIdx.y;
+  if (xb >= W) return;
+  const int16_t* drow = (const int16_t*)((const uint8_t*)disp + (size_t)y * dstride);
+  float* orow = (float*)((uint8_t*)xyz + (size_t)y * xstride);
+  const int mind = handleMissing ? *minDisp : 0;
+  float o[3 * PPT];
+  int dv[PPT];
+  if constexpr (PPT == 4) {
+    const uint2 w = *(const uint2*)(drow + xb);   // 8-byte aligned: xb is a multiple of 4 and the launcher checked the strides
+    dv[0] = (int16_t)(w.x & 0xFFFF); dv[1] = (int16_t)(w.x >> 16); dv[2] = (int16_t)(w.y & 0xFFFF); dv[3] = (int16_t)(w.y >> 16);
+  } else {
+    dv[0] = drow[xb];
+  }
 #pragma unroll
-  for (int r = 0; r < 4; r++) h[r] = Q[r * 4 + 0] * x + Q[r * 4 + 1] * y + Q[r * 4 + 2] * d + Q[r * 4 + 3];
-  float* o = (float*)((uint8_t*)xyz + (size_t)y * xstride) + (size_t)x * 3;
-  // Vec3f /= double in OpenCV multiplies by the reciprocal; explicit round-to-nearest operations (no contraction)
-  const double iw = __ddiv_rn(1.0, h[3]);
-  o[0] = (float)__dmul_rn((double)(float)h[0], iw);
-  o[1] = (float)__dmul_rn((double)(float)h[1], iw);
-  float z = (float)__dmul_rn((double)(float)h[2], iw);
-  if (handleMissing && di == *minDisp) z = 10000.f;
-  o[2] = z;
+  for (int k = 0; k < PPT; k++) {
+    const int x = xb + k, di = dv[k];
+    const double d = (double)di;
+    double h[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) h[r] = Q[r * 4 + 0] * x + Q[r * 4 + 1] * y + Q[r * 4 + 2] * d + Q[r * 4 + 3];
+    // Vec3f /= double in OpenCV multiplies by the reciprocal; explicit round-to-nearest operations (no contraction)
+    const double iw = __ddiv_rn(1.0, h[3]);
+    o[3 * k] = (float)__dmul_rn((double)(float)h[0], iw);
+    o[3 * k + 1] = (float)__dmul_rn((double)(float)h[1], iw);
+    float z = (float)__dmul_rn((double)(float)h[2], iw);
+    if (handleMissing && di == mind) z = 10000.f;
+    o[3 * k + 2] = z;
+  }
+  if constexpr (PPT == 4) {
+    float4* p = (float4*)(orow + (size_t)xb * 3);
+    p[0] = make_float4(o[0], o[1], o[2], o[3]);
+    p[1] = make_float4(o[4], o[5], o[6], o[7]);
+    p[2] = make_float4(o[8], o[9], o[10], o[11]);
+  } else {
+    orow[(size_t)xb * 3] = o[0]; orow[(size_t)xb * 3 + 1] = o[1]; orow[(size_t)xb * 3 + 2] = o[2];
+  }
 }
 
 cudaError_t launch_reproject(const int16_t* disp, size_t dstride, float* xyz, size_t xstride, int W, int H,
@@ -186,8 +209,13 @@ cudaError_t launch_reproject(const int16_t* disp, size_t dstride, float* xyz, si
     k_min_s16<<<g, 256, 0, st>>>(disp, dstride, W, H, minScratch);
     *nlaunch += 2;
   }
-  dim3 g((W + 255) / 256, H);
-  k_reproject<<<g, 256, 0, st>>>(disp, dstride, xyz, xstride, W, H, Qdev, handleMissing, minScratch);
+  if (W % 4 == 0 && ((uintptr_t)disp | dstride) % 8 == 0 && ((uintptr_t)xyz | xstride) % 16 == 0) {
+    dim3 g((W / 4 + 255) / 256, H);
+    k_reproject<4><<<g, 256, 0, st>>>(disp, dstride, xyz, xstride, W, H, Qdev, handleMissing, minScratch);
+  } else {
+    dim3 g((W + 255) / 256, H);
+    k_reproject<1><<<g, 256, 0, st>>>(disp, dstride, xyz, xstride, W, H, Qdev, handleMissing, minScratch);
+  }
   *nlaunch += 1;
   return cudaGetLastError();
 }
@@ -228,30 +256,70 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 __device__ __forceinline__ int px(const int16_t* img, size_t stride, int x, int y) {
   return *(const int16_t*)((const uint8_t*)img + (size_t)y * stride + (size_t)x * 2);
 }
-__global__ void k_spk_init(const int16_t* img, size_t stride, int W, int H, int newVal, int* L, int* sizes) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const int i = y * W + x;
-  L[i] = px(img, stride, x, y) == newVal ? -1 : i;
-  sizes[i] = 0;
+// Pass 1, one CTA per row: every valid pixel is labelled with the first pixel of its horizontal run (maximal stretch of
+// 4-connected neighbours within the row), found by a running maximum over the run breaks.  Horizontal unions are then already
+// done, and every set has a root that is at most one pointer away within its row.
+__global__ void __launch_bounds__(256) k_spk_rows(const int16_t* __restrict__ img, size_t stride, int W, int H, int newVal, int maxDiff,
+                                                  int* __restrict__ L, int* __restrict__ sizes) {
+  __shared__ int sWarp[8];
+  __shared__ int sCarry;
+  const int y = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) sCarry = -1;
+  __syncthreads();
+  for (int xb = 0; xb < W; xb += 256) {
+    const int x = xb + threadIdx.x;
+    const bool in = x < W;
+    const int v = in ? px(img, stride, x, y) : newVal;
+    const bool valid = in && v != newVal;
+    bool brk = valid;
+    if (valid && x > 0) {
+      const int q = px(img, stride, x - 1, y);
+      brk = q == newVal || abs(v - q) > maxDiff;
+    }
+    int k = brk ? x : -1;   // start of the run this pixel belongs to = the last break at or before it
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, k, o); if (lane >= o) k = max(k, t); }
+    if (lane == 31) sWarp[warp] = k;
+    __syncthreads();
+    int pre = sCarry;
+    for (int w = 0; w < warp; w++) pre = max(pre, sWarp[w]);
+    k = max(k, pre);
+    if (in) {
+      L[y * W + x] = valid ? y * W + k : -1;
+      sizes[y * W + x] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) sCarry = k;
+    __syncthreads();
+  }
 }
-__global__ void k_spk_union(const int16_t* img, size_t stride, int W, int H, int newVal, int maxDiff, int* L) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const int v = px(img, stride, x, y);
-  if (v == newVal) return;
-  const int i = y * W + x;
-  if (x > 0) { const int q = px(img, stride, x - 1, y); if (q != newVal && abs(v - q) <= maxDiff) uf_union(L, i, i - 1); }
-  if (y > 0) { const int q = px(img, stride, x, y - 1); if (q != newVal && abs(v - q) <= maxDiff) uf_union(L, i, i - W); }
+// Pass 2: vertical unions.  The edge (x,y)-(x,y-1) is skipped when the pixel to the left already joins the same two sets
+// (both rows connected to their left neighbour and the left column connected vertically).
+__global__ void __launch_bounds__(256) k_spk_vunion(const int16_t* __restrict__ img, size_t stride, int W, int H, int newVal, int maxDiff, int* L) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
+  if (x >= W || y >= H) return;
+  const int v = px(img, stride, x, y), u = px(img, stride, x, y - 1);
+  if (v == newVal || u == newVal || abs(v - u) > maxDiff) return;
+  if (x > 0) {
+    const int vl = px(img, stride, x - 1, y), ul = px(img, stride, x - 1, y - 1);
+    if (vl != newVal && ul != newVal && abs(v - vl) <= maxDiff && abs(u - ul) <= maxDiff && abs(vl - ul) <= maxDiff) return;
+  }
+  uf_union(L, y * W + x, (y - 1) * W + x);
 }
-__global__ void k_spk_count(int W, int H, int* L, int* sizes) {
+// Pass 3: flatten + component sizes.  Only "larger than maxSize or not" matters, so a counter that has passed maxSize is left
+// alone (no atomic traffic on the big components), and the lanes of a warp that share a root add once.
+__global__ void __launch_bounds__(256) k_spk_count(int W, int H, int maxSize, int* L, int* sizes) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const int i = y * W + x;
-  if (L[i] < 0) return;
-  const int r = uf_find(L, i);
-  L[i] = r;  // path compression is safe here: no unions run concurrently
-  atomicAdd(&sizes[r], 1);
+  int r = -1;
+  if (x < W) {
+    const int i = y * W + x;
+    if (L[i] >= 0) {
+      r = uf_find(L, i);
+      L[i] = r;  // path compression is safe here: no unions run concurrently
+    }
+  }
+  const unsigned m = __match_any_sync(0xFFFFFFFFu, r);
+  if (r >= 0 && (threadIdx.x & 31) == __ffs(m) - 1 && __ldcg(&sizes[r]) <= maxSize) atomicAdd(&sizes[r], __popc(m));
 }
 __global__ void k_spk_apply(int16_t* img, size_t stride, int W, int H, int newVal, int maxSize, const int* L, const int* sizes) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -262,38 +330,77 @@ __global__ void k_spk_apply(int16_t* img, size_t stride, int W, int H, int newVa
 cudaError_t launch_filter_speckles(int16_t* disp, size_t stride, int W, int H, int newVal, int maxSize, int maxDiff,
                                    int* labels, int* sizes, int* /*changed*/, cudaStream_t st, int* nlaunch) {
   dim3 g((W + 255) / 256, H);
-  k_spk_init<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, labels, sizes);
-  k_spk_union<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, maxDiff, labels);
-  k_spk_count<<<g, 256, 0, st>>>(W, H, labels, sizes);
+  k_spk_rows<<<H, 256, 0, st>>>(disp, stride, W, H, newVal, maxDiff, labels, sizes);
+  if (H > 1) {
+    dim3 gv((W + 255) / 256, H - 1);
+    k_spk_vunion<<<gv, 256, 0, st>>>(disp, stride, W, H, newVal, maxDiff, labels);
+  }
+  k_spk_count<<<g, 256, 0, st>>>(W, H, maxSize, labels, sizes);
   k_spk_apply<<<g, 256, 0, st>>>(disp, stride, W, H, newVal, maxSize, labels, sizes);
-  *nlaunch += 4;
+  *nlaunch += H > 1 ? 4 : 3;
   return cudaGetLastError();
 }
 
 // ---- cv::morphologyEx(MORPH_CLOSE, 5x5 rect) on CV_16S — src/lib.cpp:267-268 (A.13)
-template <bool DILATE>
-__global__ void __launch_bounds__(256) k_morph5(const int16_t* __restrict__ src, size_t sstride, int16_t* __restrict__ dst,
-                                                size_t dstride, int W, int H) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  int v = DILATE ? -32768 : 32767;
-  for (int dy = -2; dy <= 2; dy++) {
-    const int yy = y + dy;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = -2; dx <= 2; dx++) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= W) continue;
-      const int s = px(src, sstride, xx, yy);
-      v = DILATE ? max(v, s) : min(v, s);
-    }
+// Dilation then erosion with a 5 x 5 rectangle; pixels outside the image do not take part (OpenCV's morphology border).
+// One launch: a CTA loads its tile with a 4-pixel halo into shared memory, dilates the tile + 2-pixel halo there (rows, then
+// columns: the rectangle is separable), erodes it the same way and writes the tile: one global load and one store per pixel.
+constexpr int kMW = 64, kMH = 16, kMT = 256;   // tile and threads
+__global__ void __launch_bounds__(kMT) k_morph_close5(const int16_t* __restrict__ src, size_t sstride, int16_t* __restrict__ dst, size_t dstride,
+                                                      int W, int H) {
+  __shared__ int16_t sA[kMH + 8][kMW + 8];   // input, later the eroded rows
+  __shared__ int16_t sB[kMH + 8][kMW + 8];   // row-wise pass of the current operation
+  const int x0 = blockIdx.x * kMW - 4, y0 = blockIdx.y * kMH - 4;   // image position of sA[0][0]
+  const int16_t NEG = -32768, POS = 32767;
+  for (int i = threadIdx.x; i < (kMH + 8) * (kMW + 8); i += kMT) {
+    const int ty = i / (kMW + 8), tx = i - ty * (kMW + 8);
+    const int x = x0 + tx, y = y0 + ty;
+    sA[ty][tx] = (x >= 0 && x < W && y >= 0 && y < H) ? px(src, sstride, x, y) : NEG;   // outside: neutral for the dilation
   }
-  *(int16_t*)((uint8_t*)dst + (size_t)y * dstride + (size_t)x * 2) = (int16_t)v;
+  __syncthreads();
+  // dilation, rows: sB[ty][tx] for tx in [2, kMW + 6)
+  for (int i = threadIdx.x; i < (kMH + 8) * (kMW + 4); i += kMT) {
+    const int ty = i / (kMW + 4), tx = i - ty * (kMW + 4) + 2;
+    int v = sA[ty][tx - 2];
+#pragma unroll
+    for (int d = -1; d <= 2; d++) v = max(v, (int)sA[ty][tx + d]);
+    sB[ty][tx] = (int16_t)v;
+  }
+  __syncthreads();
+  // dilation, columns: the dilated image on rows / columns [2, +4 halo); positions outside the image become neutral for the erosion
+  for (int i = threadIdx.x; i < (kMH + 4) * (kMW + 4); i += kMT) {
+    const int ty = i / (kMW + 4) + 2, tx = i - (ty - 2) * (kMW + 4) + 2;
+    int v = sB[ty - 2][tx];
+#pragma unroll
+    for (int d = -1; d <= 2; d++) v = max(v, (int)sB[ty + d][tx]);
+    const int x = x0 + tx, y = y0 + ty;
+    sA[ty][tx] = (x >= 0 && x < W && y >= 0 && y < H) ? (int16_t)v : POS;
+  }
+  __syncthreads();
+  // erosion, rows: tx in [4, kMW + 4), ty in [2, kMH + 6)
+  for (int i = threadIdx.x; i < (kMH + 4) * kMW; i += kMT) {
+    const int ty = i / kMW + 2, tx = i - (ty - 2) * kMW + 4;
+    int v = sA[ty][tx - 2];
+#pragma unroll
+    for (int d = -1; d <= 2; d++) v = min(v, (int)sA[ty][tx + d]);
+    sB[ty][tx] = (int16_t)v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMH * kMW; i += kMT) {
+    const int ty = i / kMW + 4, tx = i - (ty - 4) * kMW + 4;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= W || y >= H) continue;
+    int v = sB[ty - 2][tx];
+#pragma unroll
+    for (int d = -1; d <= 2; d++) v = min(v, (int)sB[ty + d][tx]);
+    *(int16_t*)((uint8_t*)dst + (size_t)y * dstride + (size_t)x * 2) = (int16_t)v;
+  }
 }
-cudaError_t launch_morph_close5(const int16_t* src, size_t sstride, int16_t* tmp, int16_t* dst, size_t dstride, int W,
+// tmp is no longer needed (kept in the signature for the callers' buffers)
+cudaError_t launch_morph_close5(const int16_t* src, size_t sstride, int16_t* /*tmp*/, int16_t* dst, size_t dstride, int W,
                                 int H, cudaStream_t st) {
-  dim3 g((W + 255) / 256, H);
-  k_morph5<true><<<g, 256, 0, st>>>(src, sstride, tmp, (size_t)W * 2, W, H);
-  k_morph5<false><<<g, 256, 0, st>>>(tmp, (size_t)W * 2, dst, dstride, W, H);
+  dim3 g((W + kMW - 1) / kMW, (H + kMH - 1) / kMH);
+  k_morph_close5<<<g, kMT, 0, st>>>(src, sstride, dst, dstride, W, H);
   return cudaGetLastError();
 }
 

@@ -237,7 +237,7 @@ cudaError_t sgbm_forward(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes,
     return cudaSuccess;
   }
   if (ev) SV_RET(cudaEventRecord(ev[0], st));
-  {
+  if (left != nullptr) {   // nullptr: the operand planes are already in the scratch (front_fused.cu)
     dim3 g((W + 255) / 256, H, nframes * 2);
     const bool x4 = cn == 1 && W % 4 == 0 && ((uintptr_t)left | (uintptr_t)right | lstride | rstride | lframe | rframe) % 4 == 0;
     if (x4) {

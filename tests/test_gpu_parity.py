@@ -538,3 +538,35 @@ def test_pipeline_batch_and_streaming_match_single_calls(svgpu, oracle):
         ctx.sync()
         for o, res in zip(order, outs):
             check(res, o, "stream")
+
+
+def test_unfused_front_matches_fused(svgpu, tmp_path):
+    """The stage-by-stage kernels (k_remap, blur / gray / sharpen, k_prefilter_planes; SVGPU_UNFUSED=1, read once per process) and
+    the fused front kernel (front_fused.cu, the default for raw BGR frames) give the same disparity on the bottle pair, which
+    the golden test pins to cv2; run in a child process because the switch is read when the library first runs a pipeline."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, hashlib, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/fhgr-stereo-vision_b200"); sys.path.insert(0, sys.argv[1] + "/tests")
+import svgpu
+from helpers import golden
+from oracle import sv_oracle as oracle
+g = golden("bottle"); size = (640, 480)
+ml = oracle.init_undistort_rectify_map(g["cal_Kl"], g["cal_Dl"], g["rect_Rl"], g["rect_Pl"], size)
+mr = oracle.init_undistort_rectify_map(g["cal_Kr"], g["cal_Dr"], g["rect_Rr"], g["rect_Pr"], size)
+with svgpu.Context(*size) as ctx:
+    ctx.set_rectify_maps(0, *ml); ctx.set_rectify_maps(1, *mr); ctx.set_sgbm(**svgpu.REFERENCE_SGBM)
+    n0 = ctx.launch_count
+    out = ctx.pipeline(g["scaled_left"], g["scaled_right"], svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM, want_rect=True)
+    print("RESULT", int((out["disp"] != g["disp_raw"]).sum()), int((out["left_rect"] != g["rect_left"]).sum()), ctx.launch_count - n0)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("fused", {}), ("unfused", {"SVGPU_UNFUSED": "1"})):
+        out = subprocess.run([sys.executable, "-c", code, root], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[tag] = [int(v) for v in [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()[1:]]
+    assert res["fused"][:2] == [0, 0] and res["unfused"][:2] == [0, 0], res
+    assert res["fused"][2] < res["unfused"][2], res   # fewer kernels: 1 instead of 2 remap + 6 blur/gray/sharpen + 1 planes
