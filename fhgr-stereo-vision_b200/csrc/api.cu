@@ -116,7 +116,8 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   const int sweepFrames = way3 ? batch * 4 : batch;
   const size_t cells = g.W1 > 0 ? (size_t)g.W1 * vrows * g.D : 0;
   const size_t w1 = g.W1 > 0 ? g.W1 : 0;
-  const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2);
+  // + 256: the TMA staging of the cost kernel copies whole 16-byte units and may read one operand word past a row
+  const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2) + 256;
   const size_t need[svgpu_ctx::kScratchBufs] = {
       planeBytes, planeBytes, (size_t)batch * cells * 2, (size_t)batch * cells * 2, (size_t)batch * vrows * w1 * 8,
       (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2, 256, sgbm_flags_bytes(gs, sweepFrames), sgbm_edges_bytes(gs, sweepFrames)};

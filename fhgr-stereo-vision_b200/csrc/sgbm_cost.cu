@@ -33,12 +33,16 @@ struct CostGeom {
   int NJ;      // right-image records per row: reversed positions 0 .. NC + D - 10
   int ng;      // groups of 16 disparities
   int rowU4;   // uint4 per (row, half-group) line of the Vs buffer: NC + 1 (padding against bank conflicts)
-  size_t offL, offR, offV, offRing, total;  // byte offsets in dynamic shared memory
+  size_t offL, offR, offV, offRing, offRaw, offBar, total;  // byte offsets in dynamic shared memory
+  int nLraw, nRraw, rawSlotU2;  // TMA staging: operand words per plane of a row slot (left / right) and uint2 per slot
 };
+constexpr int kRawSlots = 3;   // row slots of the TMA staging ring: the row in use, the next one, the one in flight
 
 // CH = operand planes per image row: 2 (gradient, intensity) per colour channel
 // SRING: the pixel costs of the last 2r+1 rows live in shared memory (thread-private slots) instead of registers
-template <int NC, int RB, int CH, bool SRING>
+// TMAST: the operand words of a row tile are brought in by TMA bulk copies (cp.async.bulk + mbarrier) two rows ahead and
+//        turned into records from shared memory; otherwise every thread loads its words with LDG one row ahead
+template <int NC, int RB, int CH, bool SRING, bool TMAST>
 __host__ __device__ inline CostGeom cost_geom(int D, int R) {
   CostGeom g;
   g.ng = D / kDPL;
@@ -48,7 +52,12 @@ __host__ __device__ inline CostGeom cost_geom(int D, int R) {
   g.offR = g.offL + (size_t)2 * CH * NC * 16;        // [2 rows][CH planes][NJ] uint4
   g.offV = g.offR + (size_t)2 * CH * g.NJ * 16;      // [RB][ng*2][NC+1] uint4
   g.offRing = g.offV + (size_t)RB * g.ng * 2 * g.rowU4 * 16;   // [2R+1][words per cell block][NC x ng threads-columns] uint4
-  g.total = g.offRing + (SRING ? (size_t)(2 * R + 1) * (CH == 2 ? 1 : 2) * NC * g.ng * 16 : 0);
+  g.offRaw = g.offRing + (SRING ? (size_t)(2 * R + 1) * (CH == 2 ? 1 : 2) * NC * g.ng * 16 : 0);
+  g.nLraw = NC + 2;            // even counts: bulk copies move multiples of 16 bytes
+  g.nRraw = g.NJ + 8 + 2;
+  g.rawSlotU2 = CH * (g.nLraw + g.nRraw);
+  g.offBar = g.offRaw + (TMAST ? (size_t)kRawSlots * g.rawSlotU2 * 8 : 0);
+  g.total = g.offBar + (TMAST ? 64 : 0);
   return g;
 }
 
@@ -61,14 +70,14 @@ __device__ __forceinline__ uint32_t bt_cost(const uint4& l, const uint4& r) {
 
 // COLS neighbouring columns per thread: 8 of the 9 right-image records of two neighbouring columns are the same,
 // so two columns per thread nearly halve the shared-memory traffic of the cost arithmetic.
-template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT>
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT, bool TMAST>
 __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__ planesL, const uint2* __restrict__ planesR,
                                                                 uint4* __restrict__ Cvol, const SgbmCfg cfg, int rowsPerBand, size_t frameU4,
                                                                 int planeRows, int rowsOut) {
   constexpr int NRING = 2 * R + 1, TW = NC - 2 * R, NCP = NC / COLS;
   extern __shared__ uint4 smemU4[];
   const int D = cfg.D, W1 = cfg.W1, H = cfg.H, Wp = cfg.Wp;
-  const CostGeom G = cost_geom<NC, RB, CH, SRING>(D, R);
+  const CostGeom G = cost_geom<NC, RB, CH, SRING, TMAST>(D, R);
   uint4* sL = smemU4 + G.offL / 16;
   uint4* sRing = smemU4 + G.offRing / 16;
   uint4* sR = smemU4 + G.offR / 16;
@@ -110,6 +119,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
   //      position j = the fields of positions j and j+8 side by side.
   int itOffA[ITEMS], itOffB[ITEMS], itDst[ITEMS];  // operand index inside the row's plane block, record index (-1: none)
   uint32_t itLeft = 0;
+  // TMA staging: the words of image columns [aL, aL + nL) (left) and [aR, aR + nR) (right) of every plane of a row go into a
+  // slot of the raw ring; both ranges start at an even column (16-byte aligned source) and cover what the tile touches
+  const int xLfirst = x0 - R + cfg.minX1;
+  const int aL = max(xLfirst, 0) & ~1, bL = min(xLfirst + NC, cfg.W), nL = (bL - aL + 1) & ~1;
+  const int aR = max(xrMax - (NJ - 1) - 8, 0) & ~1, bR = min(xrMax + 1, cfg.W), nR = (bR - aR + 1) & ~1;
 #pragma unroll
   for (int q = 0; q < ITEMS; q++) {
     const int it = tid + q * nthr;
@@ -118,23 +132,35 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
     if (it < CH * NC) {
       const int ch = it / NC, cc = it % NC;
       // columns outside the volume are computed on some valid pixel and ignored by the horizontal phase
-      itOffA[q] = ch * Wp + min(max(x0 - R + cc + cfg.minX1, 0), cfg.W - 1);
+      if constexpr (TMAST) itOffA[q] = ch * G.nLraw + min(max(xLfirst + cc, aL), bL - 1) - aL;
+      else itOffA[q] = ch * Wp + min(max(xLfirst + cc, 0), cfg.W - 1);
       itDst[q] = ch * NC + lpos(cc);
       itLeft |= 1u << q;
     } else if (it < CH * NC + CH * NJ) {
       const int k = it - CH * NC, ch = k / NJ, j = k % NJ;
       // positions outside the image only ever pair with cells outside the volume: any in-range word will do
-      itOffA[q] = ch * Wp + min(max(xrMax - j, 0), cfg.W - 1);
-      itOffB[q] = ch * Wp + min(max(xrMax - j - 8, 0), cfg.W - 1);
+      if constexpr (TMAST) {
+        itOffA[q] = CH * G.nLraw + ch * G.nRraw + min(max(xrMax - j, aR), bR - 1) - aR;
+        itOffB[q] = CH * G.nLraw + ch * G.nRraw + min(max(xrMax - j - 8, aR), bR - 1) - aR;
+      } else {
+        itOffA[q] = ch * Wp + min(max(xrMax - j, 0), cfg.W - 1);
+        itOffB[q] = ch * Wp + min(max(xrMax - j - 8, 0), cfg.W - 1);
+      }
       itDst[q] = ch * NJ + rpos(j);
     }
   }
-  uint2 stA[ITEMS], stB[ITEMS];
+  auto make_left = [](const uint2 a) {
+    return make_uint4(__byte_perm(a.x, 0, 0x1010), __byte_perm(a.x, 0, 0x3232), __byte_perm(a.y, 0, 0x1010), __byte_perm(a.y, 0, 0x3232));
+  };
+  auto make_right = [](const uint2 a, const uint2 b) {
+    return make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(a.x, b.x, 0x7632), __byte_perm(a.y, b.y, 0x5410), __byte_perm(a.y, b.y, 0x7632));
+  };
+  uint2 stA[TMAST ? 1 : ITEMS], stB[TMAST ? 1 : ITEMS];
   auto stage_load = [&](int yy) {
     const uint2* rowL = pL + (size_t)yy * CH * Wp;
     const uint2* rowR = pR + (size_t)yy * CH * Wp;
 #pragma unroll
-    for (int q = 0; q < ITEMS; q++) {
+    for (int q = 0; q < (TMAST ? 0 : ITEMS); q++) {
       if (itDst[q] < 0) continue;
       if ((itLeft >> q) & 1) {
         stA[q] = __ldg(rowL + itOffA[q]);
@@ -146,14 +172,48 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
   };
   auto stage_store = [&](int b) {
 #pragma unroll
+    for (int q = 0; q < (TMAST ? 0 : ITEMS); q++) {
+      if (itDst[q] < 0) continue;
+      if ((itLeft >> q) & 1) sL[b * CH * NC + itDst[q]] = make_left(stA[q]);
+      else sR[b * CH * NJ + itDst[q]] = make_right(stA[q], stB[q]);
+    }
+  };
+  // ---- TMA staging (TMAST): thread 0 requests a row, everybody turns its words into records once they have landed
+  const uint2* sRaw = (const uint2*)(smemU4 + G.offRaw / 16);
+  uint64_t* sBar = (uint64_t*)(smemU4 + G.offBar / 16);
+  const int vbeg0 = yb - R, vend0 = ye - 1 + R;
+  const int yFirst = min(max(vbeg0, 0), H - 1), yLast = min(max(vend0, 0), H - 1);   // image rows this band reads
+  auto tma_request = [&](int yy) {   // thread 0 only
+    const int slot = (yy - yFirst) % kRawSlots;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sBar + slot);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sRaw + (size_t)slot * G.rawSlotU2);
+    const uint32_t bytes = (uint32_t)(CH * (nL + nR)) * 8u;
+    // the slot was last read (generic proxy) before the CTA barrier that precedes this call
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) {
+      const uint2* gl = pL + ((size_t)yy * CH + ch) * Wp + aL;
+      const uint2* gr = pR + ((size_t)yy * CH + ch) * Wp + aR;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)(ch * G.nLraw) * 8u),
+                   "l"(gl), "r"((uint32_t)nL * 8u), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       dst + (uint32_t)(CH * G.nLraw + ch * G.nRraw) * 8u), "l"(gr), "r"((uint32_t)nR * 8u), "r"(bar) : "memory");
+    }
+  };
+  auto tma_build = [&](int yy) {     // all threads: wait for the row, write its records into buffer yy & 1
+    const int seq = yy - yFirst, slot = seq % kRawSlots, parity = (seq / kRawSlots) & 1;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sBar + slot);
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    const uint2* raw = sRaw + (size_t)slot * G.rawSlotU2;
+    const int b = yy & 1;
+#pragma unroll
     for (int q = 0; q < ITEMS; q++) {
       if (itDst[q] < 0) continue;
-      if ((itLeft >> q) & 1)
-        sL[b * CH * NC + itDst[q]] = make_uint4(__byte_perm(stA[q].x, 0, 0x1010), __byte_perm(stA[q].x, 0, 0x3232),
-                                               __byte_perm(stA[q].y, 0, 0x1010), __byte_perm(stA[q].y, 0, 0x3232));
-      else
-        sR[b * CH * NJ + itDst[q]] = make_uint4(__byte_perm(stA[q].x, stB[q].x, 0x5410), __byte_perm(stA[q].x, stB[q].x, 0x7632),
-                                               __byte_perm(stA[q].y, stB[q].y, 0x5410), __byte_perm(stA[q].y, stB[q].y, 0x7632));
+      if ((itLeft >> q) & 1) sL[b * CH * NC + itDst[q]] = make_left(raw[itOffA[q]]);
+      else sR[b * CH * NJ + itDst[q]] = make_right(raw[itOffA[q]], raw[itOffB[q]]);
     }
   };
 
@@ -181,8 +241,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
 
   const int vbeg = yb - R, vend = ye - 1 + R;  // virtual rows whose pixel costs enter the band's sums
   int staged = min(max(vbeg, 0), H - 1);       // image row in buffer (staged & 1)
-  stage_load(staged);
-  stage_store(staged & 1);
+  if constexpr (TMAST) {
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < kRawSlots; k++)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(sBar + k)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tma_request(yFirst);
+      if (yFirst + 1 <= yLast) tma_request(yFirst + 1);
+    }
+    tma_build(staged);
+  } else {
+    stage_load(staged);
+    stage_store(staged & 1);
+  }
   __syncthreads();
   int computed = -1;                            // image row whose pixel costs are in `pix`
 
@@ -195,7 +270,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
       // ---- the next image row is staged while this one is consumed: loads now, records after the arithmetic
       const int ynext = min(max(v + 1, 0), H - 1);
       const bool doStage = v < vend && ynext != staged;
-      if (doStage) stage_load(ynext);
+      if (doStage) {
+        if constexpr (TMAST) { if (tid == 0 && ynext + 1 <= yLast) tma_request(ynext + 1); }
+        else stage_load(ynext);
+      }
       // ---- pixel costs of image row yy (rows beyond the image border repeat the border row).  Column c0 + m reads the
       //      records j0 + (COLS-1-m) + i, i = 0..7: record q of this thread serves register q - (COLS-1-m) of column m
       if (yy != computed) {
@@ -223,7 +301,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
         }
         computed = yy;
       }
-      if (doStage) { stage_store(ynext & 1); staged = ynext; }
+      if (doStage) {
+        if constexpr (TMAST) tma_build(ynext);
+        else stage_store(ynext & 1);
+        staged = ynext;
+      }
       // ---- vertical running sum: + this row, - the row that leaves the window (ring slot k)
       const int y = v - R;  // output row completed by this virtual row
 #pragma unroll
@@ -294,12 +376,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
   }
 }
 
-template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT>
+template <int R, int NC, int COLS, int RB, int ITEMS, int CH, bool SRING, int MAXT, bool TMAST = false>
 cudaError_t launch_cost(const SgbmCfg& cfg, const CostView& v, int nframes, cudaStream_t st) {
-  const CostGeom G = cost_geom<NC, RB, CH, SRING>(cfg.D, R);
+  const CostGeom G = cost_geom<NC, RB, CH, SRING, TMAST>(cfg.D, R);
   const int threads = (NC / COLS) * (cfg.D / kDPL);
   if (G.total > 227 * 1024 || threads > MAXT) return cudaErrorInvalidConfiguration;   // the callers pick configurations that fit
-  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH, SRING, MAXT>;
+  auto* k = k_cost_tile<R, NC, COLS, RB, ITEMS, CH, SRING, MAXT, TMAST>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
   if (e != cudaSuccess) return e;
   constexpr int TW = NC - 2 * R;
@@ -339,13 +421,16 @@ cudaError_t launch_cost_r(const SgbmCfg& cfg, const CostView& sc, int nframes, c
 // throughput kernel for single-channel input with blockSize <= 7 and 64..256 disparities: two neighbouring columns per thread
 // (9 instead of 16 right-image records per 16 pixel costs), the row ring in shared memory (no register spills at 128
 // registers), horizontal phase every two rows
-template <int NC, int ITEMS>
+#ifndef SV_COST_TMA
+#define SV_COST_TMA 1
+#endif
+template <int NC, int ITEMS, bool TMAST>
 cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
-    default: return launch_cost<3, NC, 2, 2, ITEMS, 2, true, 512>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    default: return launch_cost<3, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
   }
 }
 
@@ -363,10 +448,12 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes
   if (cfg.r <= 3 && cfg.D >= 64) {
     // threads = NC / 2 x D / 16 <= 512; records staged per thread and row = 2 (NC + NJ) / threads
     const int D = cfg.D;
-    if (D > 128) return launch_cost_pair<64, 2>(cfg, sc, nframes, st);
-    if (D >= 96) return launch_cost_pair<128, 2>(cfg, sc, nframes, st);
-    if (D > 64) return launch_cost_pair<128, 3>(cfg, sc, nframes, st);
-    return launch_cost_pair<256, 3>(cfg, sc, nframes, st);
+    // TMA staging of the row tiles where its three-row ring fits beside the rest (not at D = 64: 256-column tiles)
+    constexpr bool T = SV_COST_TMA != 0;
+    if (D > 128) return launch_cost_pair<64, 2, T>(cfg, sc, nframes, st);
+    if (D >= 96) return launch_cost_pair<128, 2, T>(cfg, sc, nframes, st);
+    if (D > 64) return launch_cost_pair<128, 3, T>(cfg, sc, nframes, st);
+    return launch_cost_pair<256, 3, false>(cfg, sc, nframes, st);
   }
   // one column per thread: 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
   if (cfg.D > 128) return launch_cost_r<32, 1, 8, 2>(cfg, sc, nframes, st);

@@ -75,6 +75,9 @@ namespace {
 #ifndef SV_SWEEP_LDASM
 #define SV_SWEEP_LDASM 0     // 1: operand prefetch through volatile inline PTX (keeps the loads where the source puts them)
 #endif
+#ifndef SV_SWEEP_LDPOS
+#define SV_SWEEP_LDPOS 0     // where in a pixel's code the operands of the next row are fetched: 0 top, 1 when this pixel's are dead, 2 end
+#endif
 #ifndef SV_SWEEP_FAKE
 #define SV_SWEEP_FAKE 0      // timing experiments only (results are wrong): 1 = no import from the left CTA, 2 = no export
 #endif
@@ -471,6 +474,24 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       uint4* eOut = (toRing ? outRing + (r & outMask) * ENT : wbase + G::OFF_XOUT) + gl;
       uint32_t mDLprev = 0;
       uint4 eMins = make_uint4(0, 0, 0, 0);
+      // SV_SWEEP_LDPOS = 3: the operands of the whole next row step are requested before the first pixel, into spare
+      // registers that are copied into cb / sb after the last pixel (a full row step of latency for every pixel's fetch;
+      // 4 = the same for C only, S as in 0)
+      constexpr bool EARLY_C = SV_SWEEP_LDPOS == 3 || SV_SWEEP_LDPOS == 4, EARLY_S = SECOND && SV_SWEEP_LDPOS == 3;
+      uint4 nbC[EARLY_C ? kK : 1][NV], nbS[EARLY_S ? kK : 1][NV];
+      if constexpr (EARLY_C) {
+#pragma unroll
+        for (int i = 0; i < kK; i++) {
+          const int xn = xl + i - 1;
+          const bool ld = IN_LD || (actn && (unsigned)xn < (unsigned)W1);
+          const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
+#pragma unroll
+          for (int h = 0; h < NV; h++) {
+            nbC[i][h] = ld_stream(Cf + off + h);
+            if constexpr (EARLY_S) nbS[i][h] = ld_stream(Sf + off + h);
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < kK; i++) {
         if (SV_SWEEP_PIXFENCE && i > 0) asm volatile("" ::: "memory");
@@ -486,7 +507,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           c[4 * h] = cb[i][h].x; c[4 * h + 1] = cb[i][h].y; c[4 * h + 2] = cb[i][h].z; c[4 * h + 3] = cb[i][h].w;
           if (SECOND) { sin[4 * h] = sb[i][h].x; sin[4 * h + 1] = sb[i][h].y; sin[4 * h + 2] = sb[i][h].z; sin[4 * h + 3] = sb[i][h].w; }
         }
-        {
+        // The fetch is issued once the operands of this pixel are dead (SV_SWEEP_LDPOS = 1: C after the path steps, S after the
+        // final sum; 0: at the top of the pixel), so that it can land in the registers the next row step reads them from —
+        // issued earlier it lands in spare registers and the copy at the end of the row step waits for it.
+        auto prefetch = [&](bool doC, bool doS) {
           const int xn = x - 1;
           const bool ld = IN_LD || (actn && (unsigned)xn < (unsigned)W1);
 #if SV_SWEEP_UNCOND
@@ -494,20 +518,22 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
 #pragma unroll
           for (int h = 0; h < NV; h++) {
-            cb[i][h] = ld_stream(Cf + off + h);
-            if (SECOND) sb[i][h] = ld_stream(Sf + off + h);
+            if (doC) cb[i][h] = ld_stream(Cf + off + h);
+            if (SECOND && doS) sb[i][h] = ld_stream(Sf + off + h);
           }
 #else
           if (ld) {
             const unsigned off = offNext0 + (unsigned)(i * stepU4);
 #pragma unroll
             for (int h = 0; h < NV; h++) {
-              cb[i][h] = ld_stream(Cf + off + h);
-              if (SECOND) sb[i][h] = ld_stream(Sf + off + h);
+              if (doC) cb[i][h] = ld_stream(Cf + off + h);
+              if (SECOND && doS) sb[i][h] = ld_stream(Sf + off + h);
             }
           }
 #endif
-        }
+        };
+        if (SV_SWEEP_LDPOS == 0) prefetch(true, true);
+        if (SV_SWEEP_LDPOS == 4) prefetch(false, true);
         // ---- old record of this slot: DR is used now, V one pixel later, DL two pixels later
         uint32_t oV[kNR], oDL[kNR], DRin[kNR];
         uint4* rec = rowbuf + i * REC;
@@ -572,6 +598,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           for (int q = 0; q < kNR; q++) sum[q] = __viaddmin_u16x2(sum[q], DRin[q], kMax2);
         }
 #endif
+        if (SV_SWEEP_LDPOS == 1) prefetch(true, false);
         // ---- new record of this slot (read by this worker in the next row)
 #pragma unroll
         for (int h = 0; h < NV; h++) {
@@ -612,6 +639,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
 #pragma unroll
           for (int h = 0; h < NV; h++) __stcs(Sf + off + h, make_uint4(sum[4 * h], sum[4 * h + 1], sum[4 * h + 2], sum[4 * h + 3]));
         }
+        if (SV_SWEEP_LDPOS == 1) prefetch(false, true);
+        if (SV_SWEEP_LDPOS == 2) prefetch(true, true);
         // ---- shift the delay line: what this slot held serves the next two pixels
 #pragma unroll
         for (int q = 0; q < kNR; q++) {
@@ -619,6 +648,15 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           if (HAS_V) Vd1[q] = oV[q];
         }
         mDLd2 = mDLd1; mDLd1 = omDL; mVd1 = omV;
+      }
+      if constexpr (EARLY_C) {
+#pragma unroll
+        for (int i = 0; i < kK; i++)
+#pragma unroll
+          for (int h = 0; h < NV; h++) {
+            cb[i][h] = nbC[i][h];
+            if constexpr (EARLY_S) sb[i][h] = nbS[i][h];
+          }
       }
 #if SV_SWEEP_PROF
       pfB += clock64() - pfB0;
