@@ -418,6 +418,22 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = ctx.launch_count - l0
     csum = checksum(out.cpu().numpy())
+    # Parity across GPU counts: a fixed set of frames (seeds 0 .. PAR-1, whatever N is) dealt round robin over the ranks; the sum of
+    # the per-frame checksums over all ranks must not depend on N (and is what a single GPU computes for the same frames).
+    PAR = 16 if W * H <= 1920 * 1080 else 8
+    pmine = [i for i in range(PAR) if i % world == rank]
+    psum = 0
+    if pmine and kind != "bm":
+        pl = np.empty((len(pmine), H, W), np.uint8)
+        pr = np.empty_like(pl)
+        for k, fi in enumerate(pmine):
+            pl[k], pr[k] = synth_pair(H, W, D, seed=fi)
+        if kind == "pipeline":
+            pd = ctx.pipeline_batch(torch.from_numpy(to_bgr(pl)).to(dev), torch.from_numpy(to_bgr(pr)).to(dev), ALL)["disp"]
+        else:
+            pd = ctx.sgbm_batch(torch.from_numpy(pl).to(dev), torch.from_numpy(pr).to(dev))
+        torch.cuda.synchronize()
+        psum = checksum(pd.cpu().numpy())
 
     # per-stage device time of the SGBM core of one step (CUDA events recorded inside the library on the same stream)
     stage = None
@@ -433,7 +449,8 @@ def main():
     e2e_steps = args.steps if kind == "stream" else max(3, min(args.steps, 10))
     ms_e2e = timed(step_host, e2e_steps, 2, streaming=(kind != "bm"))
 
-    stats = gather_stats([ms, ms_e2e, float(B * dev_steps), float(csum % (1 << 40))], device=dev if world > 1 else None)
+    stats = gather_stats([ms, ms_e2e, float(B * dev_steps), float(csum % (1 << 40)), float(psum % (1 << 24)), float((psum >> 24) % (1 << 24))],
+                         device=dev if world > 1 else None)
     ms_max, ms_e2e_max = float(stats[:, 0].max()), float(stats[:, 1].max())
     pairs = float(stats[:, 2].sum())
     if rank == 0:
@@ -448,7 +465,9 @@ def main():
                 "config": {"workload": cfg["workload"], "name": args.config, "pairs_per_step_per_gpu": B, "fps": pairs / (ms_max / 1e3),
                            "sharding": f"frame i -> rank i mod {world}",
                            "l2": "per-step working set (cost volumes, W1*H*D*4 bytes per pair) exceeds L2; two input sets alternate",
-                           "checksums": [int(c) for c in stats[:, 3]]},
+                           "checksums": [int(c) for c in stats[:, 3]],
+                           # sum over ranks of the checksums of frames 0 .. PAR-1 (48 bits): equal for every N
+                           "parity_checksum": int((int(stats[:, 4].sum()) + (int(stats[:, 5].sum()) << 24)) % (1 << 48)), "parity_frames": PAR},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * dev_steps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "fps": (B * world * e2e_steps) / (ms_e2e_max / 1e3), "frames": int(B * world * e2e_steps),

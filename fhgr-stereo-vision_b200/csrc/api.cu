@@ -204,6 +204,9 @@ int run_sgbm(svgpu_ctx* c, int n, const uint8_t* dl, size_t ls, size_t lf, const
   // all-invalid map instead.  Same behaviour here, as an error code.
   if (c->cfg.mode != SV_MODE_HH4 && c->W - (c->cfg.minD + c->cfg.D) <= c->cfg.r)
     return fail(c, SV_INVALID_SETTINGS, "image too narrow for minDisparity + numDisparities and blockSize");
+  // the kernels address a frame's volume with 32-bit offsets in 16-byte units
+  if ((unsigned long long)std::max(c->cfg.W1, 0) * sgbm_volume_rows(c->cfg) * c->cfg.D / 8 >= (1ull << 32))
+    return fail(c, SV_INVALID_SETTINGS, "cost volume of one pair exceeds 64 GiB");
   int rc = ensure_scratch(c, std::max(n, c->maxBatch), cn);
   if (rc) return rc;
   if (planesReady) dl = dr = nullptr;

@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_cost_tile(const uint2* __restrict__
           const uint4* line = sV + ((size_t)hrow * ng * 2 + gh) * G.rowU4;
           auto at = [&](int c) { return line[vpos(min(max(c, cLo), cHi))]; };
           const int t0 = run * RL, t1 = min(min(t0 + RL, TW), W1 - x0);
+          // (a clamp-free copy of this loop for runs that never touch the border columns, walking the two planes of a line with
+          // two pointers, measured slower: cost stage 15.9 vs 15.4 ms per 64 pairs)
           if (t0 < t1) {
             uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll

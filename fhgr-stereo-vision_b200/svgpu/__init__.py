@@ -1,8 +1,9 @@
 """svgpu — Python host side of the B200 dense-disparity path.
 
-`Context` wraps the C ABI (include/svgpu.h); `stereo_vision` mirrors the reference's public
-API (include/stereo-vision-lib/lib.hpp) on top of it.  Importing this package does not load
-the CUDA library; the first `Context()` does, and raises if it is missing (no CPU fallback).
+`Context` wraps the C ABI (include/svgpu.h), one method per entry point; the mirror of the reference's
+public C++ API (include/stereo-vision-lib/lib.hpp) is the C++23 facade under ../cpp.  Importing this
+package does not load the CUDA library; the first `Context()` does, and raises if it is missing (no
+CPU fallback).
 """
 from . import _abi
 from ._abi import (MODE_HH, MODE_HH4, MODE_SGBM, MODE_SGBM_3WAY, STAGE_DEPTH, STAGE_POSTFILTER, STAGE_PREFILTER,

@@ -525,6 +525,15 @@ def test_pipeline_batch_and_streaming_match_single_calls(svgpu, oracle):
         raw1 = ctx.pipeline(L[1], R[1], svgpu.STAGE_REMAP | svgpu.STAGE_SGBM)["disp"]
         rawb = ctx.pipeline_batch(L[:2], R[:2], svgpu.STAGE_REMAP | svgpu.STAGE_SGBM)["disp"]
         assert nmismatch(rawb[1], raw1) == 0
+        # post-filter + reprojection + depth on caller-supplied disparities (no SGBM stage), batched == single
+        dsp = np.stack([single[i]["disp"] for i in range(4)])
+        raw_in = np.stack([ctx.pipeline(L[i], R[i], svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM)["disp"] for i in range(4)])
+        post = ctx.pipeline_batch(L, R, svgpu.STAGE_POSTFILTER | svgpu.STAGE_REPROJECT | svgpu.STAGE_DEPTH, want_xyz=True, want_depth=True,
+                                  disp=raw_in.copy())
+        for i in range(4):
+            assert nmismatch(post["disp"][i], dsp[i]) == 0, i
+            assert nmismatch(post["xyz"][i].view(np.uint32), single[i]["xyz"].view(np.uint32)) == 0, i
+            assert nmismatch(post["depth"][i].view(np.uint32), single[i]["depth"].view(np.uint32)) == 0, i
         # streaming: three batches in flight, results read after sync()
         ctx.use_own_stream()
         order = [(0, 1, 2), (3, 0), (2, 3, 1)]
