@@ -20,6 +20,7 @@
 // Columns are clamped in W1 coordinates and rows in image coordinates by computing the clamped position again
 // (A.4: the window replicates the border).
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sgbm_device.cuh"
@@ -442,6 +443,21 @@ cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes, int cn, cudaStream_t st) {
   // records staged per thread and row = (CH NC + CH NJ) / threads, CH = 2 planes per colour channel
   if (cn == 3) {
+    // three channels: six operand planes, 16-bit pixel costs in the row ring.  With the ring in registers the kernel spills at
+    // 128 registers; for blockSize <= 7 and D >= 128 the ring fits into shared memory beside a two-row horizontal block
+    if (cfg.r <= 3 && cfg.D >= 128) {
+      auto go = [&](auto rtag) {
+        constexpr int RR = decltype(rtag)::value;
+        if (cfg.D > 128) return launch_cost<RR, 32, 1, 2, 6, 6, true, 512>(cfg, sc, nframes, st);
+        return launch_cost<RR, 64, 1, 2, 3, 6, true, 512>(cfg, sc, nframes, st);
+      };
+      switch (cfg.r) {
+        case 0: return go(std::integral_constant<int, 0>());
+        case 1: return go(std::integral_constant<int, 1>());
+        case 2: return go(std::integral_constant<int, 2>());
+        default: return go(std::integral_constant<int, 3>());
+      }
+    }
     if (cfg.D > 128) return launch_cost_r<32, 1, 8, 6, 6>(cfg, sc, nframes, st);
     if (cfg.D == 128) return launch_cost_r<64, 1, 8, 3, 6>(cfg, sc, nframes, st);
     if (cfg.D >= 48) return launch_cost_r<64, 1, 8, 6, 6>(cfg, sc, nframes, st);

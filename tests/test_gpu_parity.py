@@ -36,6 +36,18 @@ def test_sgbm_three_channel_golden(svgpu, oracle):
         with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
             ctx.set_sgbm(**prm)
             assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
+    # the shared-memory-ring build of the three-channel cost kernel (blockSize <= 7, D >= 128) and the register-ring build
+    # (blockSize 9) against the oracle, which the golden cases above pin to cv2
+    rng = np.random.default_rng(11)
+    for (H, W, D, bs, mode) in [(37, 330, 128, 5, 1), (33, 300, 128, 9, 0), (30, 420, 256, 3, 3), (41, 250, 160, 7, 1)]:
+        l3 = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        r3 = np.roll(l3, -9, axis=1)
+        r3[::3] = rng.integers(0, 256, r3[::3].shape, dtype=np.uint8)
+        prm = dict(REF_PARAMS, numDisparities=D, blockSize=bs, P1=8 * bs * bs, P2=32 * bs * bs, mode=mode,
+                   preFilterCap=15 if bs == 9 else 32)   # three channels at blockSize 9 only fit 16 bits with a small cap
+        with svgpu.Context(W, H) as ctx:
+            ctx.set_sgbm(**prm)
+            assert nmismatch(ctx.sgbm(l3, r3), oracle.sgbm(l3, r3, **prm)) == 0, (H, W, D, bs, mode)
     l = np.zeros((40, 200, 3), np.uint8)
     with svgpu.Context(200, 40) as ctx:
         ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=11, P1=8, P2=32, mode=1))
