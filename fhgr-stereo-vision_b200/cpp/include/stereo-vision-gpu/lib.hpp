@@ -15,6 +15,7 @@
 #include <memory>
 #include <optional>
 #include <ostream>
+#include <span>
 #include <string>
 #include <utility>
 #include <vector>
@@ -118,6 +119,14 @@ namespace stereo_vision {
     [[nodiscard]] auto AnalyzeAndAnnotateImage(Image const& left_image, Image const& right_image,
                                                std::pair<Point, Point> const& search_points) const
         -> std::expected<AnalysisResult, AnalysisError>;
+
+    /// The same for n frame pairs in one call (svgpu_pipeline_batch): what the folder loop (apps/stereo-vision/
+    /// static-image-main.cpp:107-127) and the livecam loop (livecam-main.cpp:70-106) do frame by frame.  One result per pair, in
+    /// order; a pair with an empty image yields kInvalidImage without affecting the others.  `max_in_flight` pairs are processed
+    /// per device call (scratch memory: about 1 GB per pair at 1080p / 128 disparities).
+    [[nodiscard]] auto AnalyzeAndAnnotateImages(std::span<Image const> left_images, std::span<Image const> right_images,
+                                                std::span<std::pair<Point, Point> const> search_points, int max_in_flight = 16) const
+        -> std::vector<std::expected<AnalysisResult, AnalysisError>>;
 
     /// lib.hpp:111-112 — returns a copy, like the reference.
     [[nodiscard]] Settings settings() const { return this->settings_; }

@@ -3,6 +3,7 @@
 // implementation in this file.
 #include <stereo-vision-gpu/lib.hpp>
 
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 
@@ -159,6 +160,79 @@ namespace stereo_vision {
     out.points_3d = {at(search_points.first), at(search_points.second)};
     out.depth_map = std::move(depth);
     return out;
+  }
+
+  auto StereoVision::AnalyzeAndAnnotateImages(std::span<Image const> left_images, std::span<Image const> right_images,
+                                              std::span<std::pair<Point, Point> const> search_points, int max_in_flight) const
+      -> std::vector<std::expected<AnalysisResult, AnalysisError>> {
+    std::size_t const count = std::min(left_images.size(), right_images.size());
+    std::vector<std::expected<AnalysisResult, AnalysisError>> results;
+    results.reserve(count);
+    for (std::size_t i = 0; i < count; i++) results.emplace_back(std::unexpected{AnalysisError::kInvalidImage});
+    auto const& r = this->settings_.rectification;
+    svgpu_ctx* c = this->ctx_.get();
+    auto const W = r.width, H = r.height;
+    auto const n = static_cast<std::size_t>(W) * H;
+    // frames that can go through the device: non-empty BGR pairs (the others keep their error, src/lib.cpp:54-56, 71-73)
+    std::vector<std::size_t> todo;
+    for (std::size_t i = 0; i < count; i++) {
+      if (left_images[i].empty() || right_images[i].empty()) continue;
+      if (this->settings_.algorithm != Settings::Algorithm::kSGBM || left_images[i].channels != 3 || right_images[i].channels != 3) {
+        results[i] = std::unexpected{AnalysisError::kInvalidSettings};
+        continue;
+      }
+      todo.push_back(i);
+    }
+    int const chunk = std::max(1, max_in_flight);
+    check(c, svgpu_reserve(c, chunk), "svgpu_reserve");
+    std::vector<std::uint8_t> in_l, in_r, rect_l, rect_r;
+    std::vector<std::int16_t> disp;
+    std::vector<float> xyz, depth;
+    for (std::size_t b0 = 0; b0 < todo.size(); b0 += static_cast<std::size_t>(chunk)) {
+      std::size_t const m = std::min<std::size_t>(chunk, todo.size() - b0);
+      in_l.resize(m * n * 3); in_r.resize(m * n * 3); rect_l.resize(m * n * 3); rect_r.resize(m * n * 3);
+      disp.resize(m * n); xyz.resize(m * n * 3); depth.resize(m * n);
+      // gather the frames tightly packed at calibration size (RescaleImage, src/lib.cpp:96-104, where the width differs)
+      for (std::size_t k = 0; k < m; k++) {
+        auto pack = [&](Image const& in, std::uint8_t* dst) {
+          if (in.width != W) {
+            check(c, svgpu_resize(c, in.data, in.width, in.height, in.stride, 3, dst, static_cast<std::size_t>(W) * 3, SV_MEM_HOST), "svgpu_resize");
+          } else {
+            for (int y = 0; y < H; y++)
+              std::copy_n(in.data + static_cast<std::size_t>(y) * in.stride, static_cast<std::size_t>(W) * 3, dst + static_cast<std::size_t>(y) * W * 3);
+          }
+        };
+        pack(left_images[todo[b0 + k]], in_l.data() + k * n * 3);
+        pack(right_images[todo[b0 + k]], in_r.data() + k * n * 3);
+      }
+      svgpu_pipeline_batch_io io{};
+      io.left = in_l.data(); io.right = in_r.data(); io.channels = 3;
+      io.left_rect = rect_l.data(); io.right_rect = rect_r.data();
+      io.disp = disp.data(); io.xyz = xyz.data(); io.depth = depth.data();
+      io.mem = SV_MEM_HOST;
+      int const rc = svgpu_pipeline_batch(c, static_cast<int>(m), &io,
+                                          SV_STAGE_REMAP | SV_STAGE_PREFILTER | SV_STAGE_SGBM | SV_STAGE_POSTFILTER | SV_STAGE_REPROJECT | SV_STAGE_DEPTH);
+      for (std::size_t k = 0; k < m; k++) {
+        std::size_t const i = todo[b0 + k];
+        if (rc == SV_INVALID_IMAGE) { results[i] = std::unexpected{AnalysisError::kInvalidImage}; continue; }
+        if (rc != SV_OK) { results[i] = std::unexpected{AnalysisError::kInvalidSettings}; continue; }
+        AnalysisResult out;
+        out.left_image = {std::vector<std::uint8_t>(rect_l.begin() + k * n * 3, rect_l.begin() + (k + 1) * n * 3), W, H, 3};
+        out.right_image = {std::vector<std::uint8_t>(rect_r.begin() + k * n * 3, rect_r.begin() + (k + 1) * n * 3), W, H, 3};
+        out.disparity = {std::vector<std::int16_t>(disp.begin() + k * n, disp.begin() + (k + 1) * n), W, H, 1};
+        float const* px = xyz.data() + k * n * 3;
+        auto at = [&](Point p) -> Vec3f {
+          if (p.x < 0 || p.y < 0 || p.x >= W || p.y >= H) return {0.0f, 0.0f, 0.0f};
+          float const* v = px + (static_cast<std::size_t>(p.y) * W + p.x) * 3;
+          return {v[0], v[1], v[2]};
+        };
+        auto const& sp = search_points[std::min(i, search_points.size() - 1)];
+        out.points_3d = {at(sp.first), at(sp.second)};
+        out.depth_map = Buffer<float>{std::vector<float>(depth.begin() + k * n, depth.begin() + (k + 1) * n), W, H, 1};
+        results[i] = std::move(out);
+      }
+    }
+    return results;
   }
 
 }  // namespace stereo_vision

@@ -591,3 +591,51 @@ with svgpu.Context(*size) as ctx:
         res[tag] = [int(v) for v in [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()[1:]]
     assert res["fused"][:2] == [0, 0] and res["unfused"][:2] == [0, 0], res
     assert res["fused"][2] < res["unfused"][2], res   # fewer kernels: 1 instead of 2 remap + 6 blur/gray/sharpen + 1 planes
+
+
+def test_folder_front_end_on_the_facade(svgpu, tmp_path):
+    """The reference's folder front-end (apps/stereo-vision/static-image-main.cpp:107-127: `left/`, `right/`, `calibration.yml`) on
+    the C++ facade: `folder-main` loads the calibration with LoadStereoCameraInfo, reads the frames (PPM), runs them through
+    StereoVision::AnalyzeAndAnnotateImages (svgpu_pipeline_batch) two pairs per device call and prints a checksum of every
+    disparity map: equal to the golden (cv2) post-filtered disparity of the bottle pair; an unreadable frame gives the
+    reference's 'invalid image!' for that pair only."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "fhgr-stereo-vision_b200", "cpp", "folder-main")
+    assert os.path.exists(exe), "build() compiles the facade and its programs"
+    g = golden("bottle")
+
+    def mat(name, a):
+        a = np.asarray(a, np.float64)
+        rows, cols = (a.shape if a.ndim == 2 else (1, a.size))
+        return (f"   {name}: !!opencv-matrix\n      rows: {rows}\n      cols: {cols}\n      dt: d\n      data: [ " +
+                ", ".join(repr(float(v)) for v in a.reshape(-1)) + " ]\n")
+
+    yml = ("%YAML:1.0\n---\ncalibration:\n   file_version: 1\n   image_size: [ 640, 480 ]\n" + mat("camera_matrix_left", g["cal_Kl"]) +
+           mat("camera_matrix_right", g["cal_Kr"]) + mat("dist_coeffs_left", g["cal_Dl"].reshape(1, -1)[:, :5]) +
+           mat("dist_coeffs_right", g["cal_Dr"].reshape(1, -1)[:, :5]) + mat("R", g["cal_R"]) + mat("T", g["cal_T"].reshape(3, 1)) +
+           mat("E", np.zeros((3, 3))) + mat("F", np.zeros((3, 3))) + "   reprojection_error: 0.25\n")
+    (tmp_path / "calibration.yml").write_text(yml)
+    for side, key in (("left", "scaled_left"), ("right", "scaled_right")):
+        d = tmp_path / side
+        d.mkdir()
+        rgb = np.ascontiguousarray(g[key][:, :, ::-1])
+        for i in range(3):
+            with open(d / f"frame_{i}.ppm", "wb") as f:
+                f.write(b"P6\n640 480\n255\n" + rgb.tobytes())
+        (d / "frame_3.ppm").write_bytes(b"not an image")
+    out = subprocess.run([exe, str(tmp_path), str(tmp_path / "calibration.yml"), "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+    def fnv(a):
+        h = 1469598103934665603
+        for b in np.ascontiguousarray(a).tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    want = fnv(g["disp_post"])
+    sums = [int(l.split("disparity checksum")[1]) for l in out.stdout.splitlines() if "disparity checksum" in l]
+    assert sums == [want, want, want], out.stdout
+    assert "frame_3.ppm / frame_3.ppm: error: invalid image!" in out.stdout
+    assert "4 pairs in" in out.stdout
