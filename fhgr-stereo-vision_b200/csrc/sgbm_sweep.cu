@@ -112,7 +112,13 @@ struct SweepGeom {
   static constexpr int WTA = SECOND ? VEC : 0;    // per worker: final S of one pixel (neighbour lookup)
   static constexpr int OFF_RING = RW * ROWBUF;    // in-warp rings of workers 1..RW-1, then the ring of worker 0
   static constexpr int OFF_RING0 = OFF_RING + (RW - 1) * kRingI * ENT;
-  static constexpr int OFF_XOUT = OFF_RING0 + kRingX * ENT;  // export of the last worker when it does not go to a ring
+  // Import ring of a warp's first worker and the publication period across CTAs.  At 16 lanes per pixel (D > 128) an entry is
+  // 2 KB and the 8-deep ring would leave room for 6 warps only: 4 entries, published every 2 rows, keep all 8 warps.
+  static constexpr int RINGX = LPP == 16 ? 4 : kRingX;
+  static constexpr int PUB = LPP == 16 ? 2 : kPub;
+  static constexpr int AHEAD = LPP == 16 ? RINGX - 1 : kAhead;
+  static_assert(RINGX % PUB == 0 && RINGX >= PUB + 2 && AHEAD < RINGX, "import blocks must tile the ring and leave room for the two entries in use");
+  static constexpr int OFF_XOUT = OFF_RING0 + RINGX * ENT;  // export of the last worker when it does not go to a ring
   static constexpr int OFF_WTA = OFF_XOUT + ENT;
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
   static constexpr int STAGE_U4 = 1;               // the mbarrier of the TMA copies from the left CTA's entries
@@ -265,9 +271,9 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
   uint4* wbase = smem + warp * G::WARP_U4;
   uint4* rowbuf = wbase + j * G::ROWBUF + gl;  // lane-private: [pixel][path][half][gl]
   uint4* inRing = wbase + (j > 0 ? G::OFF_RING + (j - 1) * kRingI * ENT : G::OFF_RING0);
-  const int inMask = j > 0 ? kRingI - 1 : kRingX - 1;
+  const int inMask = j > 0 ? kRingI - 1 : G::RINGX - 1;
   uint4* outRing = (j < RW - 1) ? wbase + G::OFF_RING + j * kRingI * ENT : wbase + G::WARP_U4 + G::OFF_RING0;
-  const int outMask = (j < RW - 1) ? kRingI - 1 : kRingX - 1;
+  const int outMask = (j < RW - 1) ? kRingI - 1 : G::RINGX - 1;
   uint4* ring0 = wbase + G::OFF_RING0;
   uint16_t* wta = (uint16_t*)(wbase + G::OFF_WTA + j * G::WTA);
 
@@ -358,14 +364,14 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         if (!leftGlobal) {
           { PF_BEGIN; ok = wait_cta(&sProg[warp - 1], need, sAbort, a.status); PF_END(pfLeft); }
         } else {
-          // The left CTA publishes a row count after a fence every kPub rows; published entries are copied straight into
-          // this warp's ring by the TMA in blocks of up to kPub rows (row-aligned like the publications), ahead of use.
-          auto blockEnd = [&](int from) { return min((from / kPub) * kPub + kPub, y1p + 1); };
+          // The left CTA publishes a row count after a fence every G::PUB rows; published entries are copied straight into
+          // this warp's ring by the TMA in blocks of up to G::PUB rows (row-aligned like the publications), ahead of use.
+          auto blockEnd = [&](int from) { return min((from / G::PUB) * G::PUB + G::PUB, y1p + 1); };
           auto issue = [&](int from, int to) {
             __syncwarp();
             if (lane == 0) {
               fence_proxy_async_global();
-              bulk_load(ring0 + (from & (kRingX - 1)) * ENT, gin + (size_t)from * ENT, (uint32_t)(to - from) * (ENT * 16), sBar);
+              bulk_load(ring0 + (from & (G::RINGX - 1)) * ENT, gin + (size_t)from * ENT, (uint32_t)(to - from) * (ENT * 16), sBar);
             }
           };
           auto finish = [&]() {  // wait for the block in flight
@@ -402,10 +408,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
             barPhase ^= 1;
             loaded = pendEnd;
           }
-          // request the next block (entries T-1 and T are in use, so rows up to T + kRingX - 2 have a free slot)
+          // request the next block (entries T-1 and T are in use, so rows up to T + G::RINGX - 2 have a free slot)
           if (ok && pendEnd <= loaded && loaded <= y1p) {
             const int be = blockEnd(loaded);
-            if (be - 1 <= T + kRingX - 2) {
+            if (be - 1 <= T + G::RINGX - 2) {
               if (gseen < be) {
                 // the count is polled with a relaxed load one step ahead (no stall); only when that hint says the block
                 // is there is it confirmed with an acquire load, which orders the copy below behind the publication
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           }
         }
       }
-      if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - kAhead, sAbort, a.status); PF_END(pfRight); }
+      if (hasRight && actL && !rightGlobal && ok) { where = 2; PF_BEGIN; ok = wait_cta(&sCons[warp + 1], rL - G::AHEAD, sAbort, a.status); PF_END(pfRight); }
       if (!ok) break;
 #if SV_SWEEP_PROF
       const long long pfq5 = clock64();
@@ -671,7 +677,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
           for (int h = 0; h < NV; h++) __stcg(gOut + v * VEC + h * LPP, eOut[v * VEC + h * LPP]);
         if (gl == 0) __stcg(gOut - gl + 4 * VEC, eMins);
       }
-      if (rightGlobal && actL && ((rL % kPub) == kPub - 1 || rL == y1L)) {
+      if (rightGlobal && actL && ((rL % G::PUB) == G::PUB - 1 || rL == y1L)) {
         // publish: the warp barrier orders every lane's entry stores before lane 0's release store of the counter (the
         // release also waits for the warp's outstanding prefetch loads, which is why it is not done for every row)
         __syncwarp();

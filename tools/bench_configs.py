@@ -39,7 +39,7 @@ if __name__ == "__main__":
     if "--latency" in sys.argv:   # one pair per call, the way the reference's front-ends call the library
         for (W, H, D, mode, name) in [(640, 480, 224, 3, "reference 640x480 D=224 HH4"), (1280, 720, 64, 0, "config 2 1280x720 D=64 SGBM"),
                                       (1920, 1080, 128, 1, "config 3 1920x1080 D=128 HH"), (3840, 2160, 256, 1, "config 4 3840x2160 D=256 HH")]:
-            for B in (1, 2, 4):
+            for B in ((1, 2, 4, 8, 16, 32) if W < 3840 else (1, 2, 4, 8)):
                 fps, _ = sgbm(W, H, D, mode, B)
                 print(f"{name}: {B} pair(s) per call: {B / fps * 1e3:7.2f} ms per call, {fps:7.1f} fps", flush=True)
         sys.exit(0)
