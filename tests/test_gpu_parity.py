@@ -639,3 +639,29 @@ def test_folder_front_end_on_the_facade(svgpu, tmp_path):
     assert sums == [want, want, want], out.stdout
     assert "frame_3.ppm / frame_3.ppm: error: invalid image!" in out.stdout
     assert "4 pairs in" in out.stdout
+
+
+def test_medium_batch_odd_count_speckle_and_streaming(svgpu, oracle):
+    """Seven pairs per call (an odd count, all in one chunk): every pair equals the oracle on host and on device buffers, with
+    the speckle filter behind the batch, for a sub-batch of the same context and through two overlapping streamed calls."""
+    import torch
+    from svgpu.synth import synth_batch
+    H, W, D, n = 70, 300, 64, 7
+    L, R = synth_batch(n, H, W, D, seed0=70)
+    for mode, spk in ((1, 0), (3, 60)):
+        prm = dict(REF_PARAMS, numDisparities=D, mode=mode, speckleWindowSize=spk, speckleRange=2 if spk else 0)
+        want = np.stack([oracle.sgbm(L[i], R[i], **prm) for i in range(n)])
+        with svgpu.Context(W, H) as ctx:
+            ctx.set_sgbm(**prm)
+            ctx.reserve(n)
+            assert nmismatch(ctx.sgbm_batch(L, R), want) == 0
+            td = ctx.sgbm_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda())
+            torch.cuda.synchronize()
+            assert nmismatch(td.cpu().numpy(), want) == 0
+            assert nmismatch(ctx.sgbm_batch(L[:4], R[:4]), want[:4]) == 0
+            ctx.use_own_stream()
+            outs = [np.zeros((n, H, W), np.int16) for _ in range(2)]
+            for o in outs:
+                ctx.sgbm_enqueue(L, R, o)
+            ctx.sync()
+            assert nmismatch(outs[0], want) == 0 and nmismatch(outs[1], want) == 0
