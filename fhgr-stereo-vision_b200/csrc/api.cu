@@ -151,7 +151,8 @@ int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
   if (p.numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported");
   if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4 && p.mode != SV_MODE_SGBM_3WAY)
     return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH, MODE_SGBM_3WAY or MODE_HH4");
-  if (p.blockSize > 11 || (p.blockSize > 0 && p.blockSize % 2 == 0)) return fail(c, SV_INVALID_SETTINGS, "blockSize must be odd and <= 11");
+  // 15 x 15 is the largest block whose cost fits 16 bits at all (225 x 93 + P2, checked below)
+  if (p.blockSize > 15 || (p.blockSize > 0 && p.blockSize % 2 == 0)) return fail(c, SV_INVALID_SETTINGS, "blockSize must be odd and <= 15");
   if (p.preFilterCap > 63) return fail(c, SV_INVALID_SETTINGS, "preFilterCap must be <= 63");
   g.W = c->W; g.H = c->H;
   g.D = p.numDisparities; g.minD = p.minDisparity;

@@ -427,13 +427,13 @@ cudaError_t launch_cost_r(const SgbmCfg& cfg, const CostView& sc, int nframes, c
 #ifndef SV_COST_TMA
 #define SV_COST_TMA 1
 #endif
-template <int NC, int ITEMS, bool TMAST>
+template <int NC, int ITEMS, bool TMAST, int RB = 2>
 cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes, cudaStream_t st) {
   switch (cfg.r) {
-    case 0: return launch_cost<0, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
-    case 1: return launch_cost<1, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
-    case 2: return launch_cost<2, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
-    default: return launch_cost<3, NC, 2, 2, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    case 0: return launch_cost<0, NC, 2, RB, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    case 1: return launch_cost<1, NC, 2, RB, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    case 2: return launch_cost<2, NC, 2, RB, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
+    default: return launch_cost<3, NC, 2, RB, ITEMS, 2, true, 512, TMAST>(cfg, sc, nframes, st);
   }
 }
 
@@ -442,6 +442,19 @@ cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes
 // Ctrue of `nframes` pairs from their pre-filter planes
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes, int cn, cudaStream_t st) {
   // records staged per thread and row = (CH NC + CH NJ) / threads, CH = 2 planes per colour channel
+  if (cfg.r >= 6) {
+    // blockSize 13 / 15 (the 16-bit cost contract admits nothing larger, and single-channel input only): the general build with
+    // its 13- / 15-row ring in shared memory and a two-row horizontal block
+    auto go = [&](auto rtag) {
+      constexpr int RR = decltype(rtag)::value;
+      if (cfg.D > 128) return launch_cost<RR, 32, 1, 2, 2, 2, true, 512>(cfg, sc, nframes, st);
+      if (cfg.D == 128) return launch_cost<RR, 64, 1, 2, 1, 2, true, 512>(cfg, sc, nframes, st);
+      if (cfg.D >= 48) return launch_cost<RR, 64, 1, 2, 2, 2, true, 512>(cfg, sc, nframes, st);
+      return launch_cost<RR, 64, 1, 2, 5, 2, true, 512>(cfg, sc, nframes, st);
+    };
+    if (cn != 1 || cfg.r > 7) return cudaErrorInvalidConfiguration;
+    return cfg.r == 6 ? go(std::integral_constant<int, 6>()) : go(std::integral_constant<int, 7>());
+  }
   if (cn == 3) {
     // three channels: six operand planes, 16-bit pixel costs in the row ring.  With the ring in registers the kernel spills at
     // 128 registers; for blockSize <= 7 and D >= 128 the ring fits into shared memory beside a two-row horizontal block
@@ -466,12 +479,13 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes
   if (cfg.r <= 3 && cfg.D >= 64) {
     // threads = NC / 2 x D / 16 <= 512; records staged per thread and row = 2 (NC + NJ) / threads
     const int D = cfg.D;
-    // TMA staging of the row tiles where its three-row ring fits beside the rest (not at D = 64: 256-column tiles)
+    // TMA staging of the row tiles; at D = 64 (256-column tiles) its three-row ring only fits beside a one-row horizontal block
     constexpr bool T = SV_COST_TMA != 0;
+    // (a one-row horizontal block measured slower where the two-row one fits: cost stage 15.6 vs 15.4 ms at D = 128)
     if (D > 128) return launch_cost_pair<64, 2, T>(cfg, sc, nframes, st);
     if (D >= 96) return launch_cost_pair<128, 2, T>(cfg, sc, nframes, st);
     if (D > 64) return launch_cost_pair<128, 3, T>(cfg, sc, nframes, st);
-    return launch_cost_pair<256, 3, false>(cfg, sc, nframes, st);
+    return launch_cost_pair<256, 3, T, 1>(cfg, sc, nframes, st);   // cost stage 5.04 -> 3.86 ms per 64 pairs at 1280x720 / 64
   }
   // one column per thread: 64 columns per tile while the CTA stays within 512 threads (D <= 128), 32 columns above
   if (cfg.D > 128) return launch_cost_r<32, 1, 8, 2>(cfg, sc, nframes, st);

@@ -665,3 +665,22 @@ def test_medium_batch_odd_count_speckle_and_streaming(svgpu, oracle):
                 ctx.sgbm_enqueue(L, R, o)
             ctx.sync()
             assert nmismatch(outs[0], want) == 0 and nmismatch(outs[1], want) == 0
+
+
+def test_sgbm_block_sizes_13_and_15(svgpu, oracle):
+    """blockSize 13 / 15 (row ring of the cost kernel in shared memory; everything above 15 cannot fit the 16-bit cost range and is
+    refused like any other overflowing parameter set): bit-exact against the oracle, which test_oracle.py pins to cv2 for these."""
+    rng = np.random.default_rng(1315)
+    for bs, mode, D, H, W in ((13, 0, 32, 60, 190), (13, 1, 128, 50, 420), (15, 3, 64, 70, 300), (15, 1, 256, 40, 460), (13, 3, 16, 33, 90)):
+        l = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        r = np.roll(l, -5, axis=1)
+        r = np.clip(r.astype(int) + rng.integers(-6, 7, r.shape), 0, 255).astype(np.uint8)
+        prm = dict(REF_PARAMS, numDisparities=D, blockSize=bs, P1=100, P2=400, preFilterCap=15, uniquenessRatio=10, mode=mode)
+        with svgpu.Context(W, H) as ctx:
+            ctx.set_sgbm(**prm)
+            assert nmismatch(ctx.sgbm(l, r), oracle.sgbm(l, r, **prm)) == 0, (bs, mode, D)
+    with svgpu.Context(200, 60) as ctx:
+        with pytest.raises(svgpu.SvgpuError):
+            ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=17, P1=8, P2=32, preFilterCap=15, mode=1))
+        with pytest.raises(svgpu.SvgpuError):   # 15 x 15 x (2 x 33 + 63) + P2 leaves the 16-bit cost range
+            ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=15, P2=4000, mode=1))

@@ -132,3 +132,17 @@ def test_live_cv2_random(oracle, cv2):
         assert nmismatch(oracle.sgbm(l, r, **prm), s.compute(l, r)) == 0, prm
         d = s.compute(l, r)
         assert nmismatch(oracle.median3(d), cv2.medianBlur(d, 3)) == 0
+
+
+def test_live_cv2_large_blocks(oracle, cv2):
+    """blockSize 13 and 15 (the largest whose cost fits OpenCV's 16-bit cost type with a small pre-filter cap): oracle == cv2."""
+    rng = np.random.default_rng(1315)
+    for bs, mode, D in ((13, 0, 32), (13, 1, 48), (15, 3, 32), (15, 1, 16)):
+        H, W = 40 + bs, 150 + D
+        l = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        r = np.roll(l, -5, axis=1)
+        r = np.clip(r.astype(int) + rng.integers(-6, 7, r.shape), 0, 255).astype(np.uint8)
+        prm = dict(minDisparity=0, numDisparities=D, blockSize=bs, P1=100, P2=400, disp12MaxDiff=1, preFilterCap=15,
+                   uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=mode)
+        assert bs * bs * (2 * 15 + 63) + 400 <= 32767
+        assert nmismatch(oracle.sgbm(l, r, **prm), cv2.StereoSGBM_create(**prm).compute(l, r)) == 0, prm
