@@ -63,3 +63,21 @@ def test_shard_frames_rejects_bad_rank():
     from svgpu.sharding import shard_frames
     with pytest.raises(ValueError):
         shard_frames(4, 2, 2)
+
+
+def test_parity_checksum_is_independent_of_the_gpu_count():
+    """bench.py's `parity_checksum`: every rank sends the two 24-bit halves of the checksum of its share of a fixed frame set; the
+    recombined sum over the ranks (mod 2^48) is the same for 1, 2, 4 and 8 ranks and equals the unsharded checksum."""
+    sys.path.insert(0, os.path.join(ROOT, "fhgr-stereo-vision_b200"))
+    from svgpu.sharding import checksum, shard_frames
+    rng = np.random.default_rng(8)
+    frames = rng.integers(-16, 4000, (16, 9, 11)).astype(np.int16)
+    want = checksum(frames) % (1 << 48)
+    for world in (1, 2, 4, 8):
+        lo = hi = 0.0
+        for rank in range(world):
+            mine = shard_frames(16, rank, world)
+            p = checksum(frames[mine])
+            lo += float(p % (1 << 24))                  # what the rank contributes to the float64 all_gather
+            hi += float((p >> 24) % (1 << 24))
+        assert (int(lo) + (int(hi) << 24)) % (1 << 48) == want, world
