@@ -899,7 +899,14 @@ SVGPU_API int svgpu_pipeline(svgpu_ctx* c, const svgpu_pipeline_io* io, unsigned
   }
   rc = pipeline_device(c, 1, p, stages);
   if (rc) return rc;
-  if (!host) return SV_OK;
+  if (!host) {
+    // device buffers: with only one of the two rectified outputs requested the pair was rectified into the context's scratch
+    if ((stages & SV_STAGE_REMAP) && (io->left_rect != nullptr) != (io->right_rect != nullptr)) {
+      uint8_t* dst = io->left_rect ? io->left_rect : io->right_rect;
+      CU(c, cudaMemcpy2DAsync(dst, io->rect_stride, io->left_rect ? p.rectL : p.rectR, p.rectS, W * cn, H, cudaMemcpyDeviceToDevice, c->st));
+    }
+    return SV_OK;
+  }
   if (stages & SV_STAGE_REMAP) {
     if (io->left_rect) { rc = d2h_2d(c, io->left_rect, io->rect_stride, p.rectL, p.rectS, W * cn, (int)H); if (rc) return rc; }
     if (io->right_rect) { rc = d2h_2d(c, io->right_rect, io->rect_stride, p.rectR, p.rectS, W * cn, (int)H); if (rc) return rc; }

@@ -1,8 +1,9 @@
 #!/bin/bash
 # Multi-GPU bench lines of the 4K full chain and the 10,000-frame stream (BASELINE configs[3], [4]) on N GPUs of one box.
-# usage (through gpurun --gpus N): bash tools/gpu_multi.sh N
-N="$1"; O=gpurun_out; mkdir -p $O
-for cfg in 4k256_pipeline stream10k; do
+# usage (through gpurun --gpus N): bash tools/gpu_multi.sh N [configs...]   (default: 4k256_pipeline stream10k)
+N="$1"; shift; O=gpurun_out; mkdir -p $O
+CFGS="${@:-4k256_pipeline stream10k}"
+for cfg in $CFGS; do
   if [ "$N" = 1 ]; then
     timeout 900 python bench.py --gpus 1 --config $cfg --steps 5 --warmup 3 --no-cpu > $O/multi_${cfg}_n$N.json 2> $O/multi_${cfg}_n$N.err
   else
