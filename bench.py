@@ -146,6 +146,12 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
+def workload_config(name, cfg):
+    """The `config` object of the JSON line: identical for the CUDA arm and the reference arm of one workload."""
+    return {"workload": cfg["workload"], "name": name, "width": cfg["W"], "height": cfg["H"], "num_disparities": cfg["D"],
+            "l2": "per-step working set (cost volumes, W1*H*D*4 bytes per pair in flight) exceeds L2; two input sets alternate"}
+
+
 def sgbm_params(cfg):
     return dict(REF, numDisparities=cfg["D"], mode=cfg["mode"])
 
@@ -263,8 +269,8 @@ def run_reference(args, cfg):
     value = n * args.steps * mpd / t
     line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "name": args.config, "pairs_per_step": n, "fps": n * args.steps / t},
+            "vs_baseline": None, "dtype": "s16", "data": "synthetic", "fps": n * args.steps / t,
+            "config": workload_config(args.config, cfg), "details": {"pairs_per_step": n, "fps": n * args.steps / t},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.workers, "kind": cpu.kind, "sample": desc, "cpu_model": cpu_info()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -461,20 +467,21 @@ def main():
         hbm_peak, which = peaks()
         line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": dev_steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / dev_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "s16", "data": "synthetic",
-                "config": {"workload": cfg["workload"], "name": args.config, "pairs_per_step_per_gpu": B, "fps": pairs / (ms_max / 1e3),
-                           "sharding": f"frame i -> rank i mod {world}",
-                           "l2": "per-step working set (cost volumes, W1*H*D*4 bytes per pair) exceeds L2; two input sets alternate",
-                           "checksums": [int(c) for c in stats[:, 3]],
-                           # sum over ranks of the checksums of frames 0 .. PAR-1 (48 bits): equal for every N
-                           "parity_checksum": int((int(stats[:, 4].sum()) + (int(stats[:, 5].sum()) << 24)) % (1 << 48)), "parity_frames": PAR},
+                "dtype": "s16", "data": "synthetic", "fps": pairs / (ms_max / 1e3),
+                # `config` names the workload and is the same dictionary in both arms (this one and --impl reference);
+                # what differs per run is under `details`
+                "config": workload_config(args.config, cfg),
+                "details": {"pairs_per_step_per_gpu": B, "fps": pairs / (ms_max / 1e3), "sharding": f"frame i -> rank i mod {world}",
+                            "checksums": [int(c) for c in stats[:, 3]],
+                            # sum over ranks of the checksums of frames 0 .. PAR-1 (48 bits): equal for every N
+                            "parity_checksum": int((int(stats[:, 4].sum()) + (int(stats[:, 5].sum()) << 24)) % (1 << 48)), "parity_frames": PAR},
                 "clocks": clocks, "gpu_launches": int(launches_per_step * dev_steps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "fps": (B * world * e2e_steps) / (ms_e2e_max / 1e3), "frames": int(B * world * e2e_steps),
                         "api": {"pipeline": "svgpu_pipeline_enqueue_batch + svgpu_sync", "bm": "svgpu_bm_compute with host buffers"}.get(
                             kind, "svgpu_sgbm_enqueue_batch + svgpu_sync") + " on pinned host buffers (copy-in / kernels / copy-out of consecutive steps overlap)"}}
         if kind == "stream":
-            line["config"]["note"] = value_note
+            line["details"]["note"] = value_note
         if stage is not None:
             cells = (W - D) * H * D
             # Dominant kernel: k_sweep (path aggregation + WTA), two launches per step (forward and reverse sweep).  Algorithmic

@@ -20,7 +20,7 @@ for cfg in 720p64 ref_hh4 bm720p 4k256_pipeline stream10k; do
 import json, sys
 try:
     d = json.loads([l for l in open(sys.argv[2]) if l.startswith('{')][-1])
-    print(sys.argv[1], "fps", round(d['config']['fps'], 1), "e2e fps", round(d['e2e']['fps'], 1), "cpu", round(d.get('cpu_baseline', {}).get('value', 0)), "value", round(d['value']))
+    print(sys.argv[1], "fps", round(d['details']['fps'], 1), "e2e fps", round(d['e2e']['fps'], 1), "cpu", round(d.get('cpu_baseline', {}).get('value', 0)), "value", round(d['value']))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY

@@ -14,7 +14,7 @@ for cfg in $CFGS; do
 import json, sys
 try:
     d = json.loads([l for l in open(sys.argv[3]) if l.startswith('{')][-1])
-    print(sys.argv[1], "N =", sys.argv[2], "fps", round(d['config']['fps'], 1), "e2e fps", round(d['e2e']['fps'], 1), "parity", d['config']['parity_checksum'])
+    print(sys.argv[1], "N =", sys.argv[2], "fps", round(d['details']['fps'], 1), "e2e fps", round(d['e2e']['fps'], 1), "parity", d['details']['parity_checksum'])
 except Exception as e:
     print(sys.argv[1], sys.argv[2], "FAILED", e)
 PY
