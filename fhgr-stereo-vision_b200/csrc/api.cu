@@ -44,6 +44,8 @@ struct svgpu_ctx {
   int* minScratch = nullptr;
   // streaming entry point: copy-in / compute / copy-out of consecutive enqueues overlap (double-buffered staging)
   cudaStream_t stIn = nullptr, stOut = nullptr;
+  cudaStream_t stAux = nullptr;                  // second aggregation pass of a few pairs (sgbm_sweep.cu)
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   Buf pipeL[2], pipeR[2], pipeD[2], pipeX[2], pipeZ[2], pipeRL[2], pipeRR[2];
   cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
   unsigned long long enqueued = 0;
@@ -119,12 +121,17 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   // + 256: the TMA staging of the cost kernel copies whole 16-byte units and may read one operand word past a row
   const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2) + 256;
   const size_t need[svgpu_ctx::kScratchBufs] = {
-      planeBytes, planeBytes, (size_t)batch * cells * 2, (size_t)batch * cells * 2, (size_t)batch * vrows * w1 * 8,
+      planeBytes, planeBytes, (size_t)batch * cells * 2, (way3 ? (size_t)batch : sgbm_s_frames(gs, batch)) * cells * 2, (size_t)batch * vrows * w1 * 8,
       (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2, 256, sgbm_flags_bytes(gs, sweepFrames), sgbm_edges_bytes(gs, sweepFrames)};
   bool fits = c->sc.dispRaw != nullptr;
   for (int i = 0; i < svgpu_ctx::kScratchBufs; i++) fits = fits && c->allocBytes[i] >= need[i];
-  if (fits) {
+  auto publish = [&] {
     c->sc.frameCells = cells;
+    c->sc.aux = c->stAux; c->sc.evFork = c->evFork; c->sc.evJoin = c->evJoin;
+    c->sc.sBytes = c->allocBytes[3]; c->sc.flagBytes = c->allocBytes[7]; c->sc.edgeBytes = c->allocBytes[8];
+  };
+  if (fits) {
+    publish();
     return SV_OK;
   }
   // work that still uses the old buffers must be done before they go away
@@ -141,7 +148,7 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   cudaMemsetAsync(c->sc.status, 0, want[6], c->st);
   cudaMemsetAsync(c->sc.flags, 0, want[7], c->st);
   cudaMemsetAsync(c->sc.edges, 0, want[8], c->st);
-  c->sc.frameCells = cells;
+  publish();
   return SV_OK;
 }
 
@@ -377,6 +384,12 @@ SVGPU_API int svgpu_create(int device, int width, int height, svgpu_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SV_CUDA_ERROR; }
   c->st = c->own;
   for (auto& e : c->ev) cudaEventCreate(&e);
+  if (cudaStreamCreateWithFlags(&c->stAux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) != cudaSuccess) {
+    svgpu_destroy(c);
+    return SV_CUDA_ERROR;
+  }
   if (cudaMalloc((void**)&c->Qdev, 16 * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&c->minScratch, 256) != cudaSuccess) {
     svgpu_destroy(c);
     return SV_OOM;
@@ -402,6 +415,8 @@ SVGPU_API int svgpu_destroy(svgpu_ctx* c) {
   }
   if (c->stIn) { cudaStreamSynchronize(c->stIn); cudaStreamDestroy(c->stIn); }
   if (c->stOut) { cudaStreamSynchronize(c->stOut); cudaStreamDestroy(c->stOut); }
+  if (c->stAux) { cudaStreamSynchronize(c->stAux); cudaStreamDestroy(c->stAux); }
+  for (cudaEvent_t e : {c->evFork, c->evJoin}) if (e) cudaEventDestroy(e);
   if (c->own) cudaStreamDestroy(c->own);
   delete c;
   return SV_OK;

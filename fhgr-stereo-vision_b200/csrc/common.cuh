@@ -44,6 +44,11 @@ struct SgbmScratch {
   unsigned long long* flags;  // inter-CTA progress flags of the sweep kernels
   uint16_t* edges;    // inter-CTA edge exchange of the sweep kernels
   size_t frameCells;  // W1*H*D
+  // the two aggregation passes of a few pairs run side by side (sgbm_sweep.cu): second stream, fork / join events and the
+  // capacities of S, flags and edges in bytes (0 / null: passes run one after the other)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  size_t sBytes = 0, flagBytes = 0, edgeBytes = 0;
 };
 
 // MODE_SGBM_3WAY (OpenCV's computeDisparity3WAY; restated in oracle/sv_oracle_sgbm.c: sgbm_3way) cuts the image into four
@@ -94,6 +99,7 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& view, int nfram
 // sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats, int cn = 1);
+size_t sgbm_s_frames(const SgbmCfg& cfg, int nframes);   // S volumes that `nframes` pairs per call need
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);
 

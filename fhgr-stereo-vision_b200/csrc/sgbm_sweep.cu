@@ -97,18 +97,18 @@ constexpr unsigned long long kWaitLimitNs = 10000000000ull;  // a hand-over that
 constexpr int kFlagBytes = 256;   // hand-over counters, ticket and abort flag at the end of shared memory
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kMaxNW = SV_SWEEP_MAXNW;      // 8 warps = 256 threads leave the sweep kernels the full 255 registers per thread
-constexpr int kLowNW = 4;                   // latency variant for a few pairs per call: one warp per scheduler, twice the strip groups
+constexpr int kLowK = 2;                    // latency variant for a few pairs per call: strips of 2 columns (a shorter wavefront, more strip groups)
 
 enum : int { P_H = 1, P_DL = 2, P_V = 4, P_DR = 8 };
 
-template <int LPP, bool SECOND, int MAXNW = kMaxNW>
+template <int LPP, bool SECOND, int K = kK>
 struct SweepGeom {
   static constexpr int RW = 32 / LPP;             // workers (strips) per warp
   static constexpr int NV = kNR / 4;              // uint4 per lane per path vector
   static constexpr int VEC = LPP * NV;            // uint4 per path vector of one pixel
   static constexpr int REC = 3 * VEC;             // record of one pixel: V, DL, DR
   static constexpr int ENT = 4 * VEC + 1;         // hand-over entry of one row: H, V1, DL1, DL0, mins
-  static constexpr int ROWBUF = kK * REC;         // per worker
+  static constexpr int ROWBUF = K * REC;         // per worker
   static constexpr int WTA = SECOND ? VEC : 0;    // per worker: final S of one pixel (neighbour lookup)
   static constexpr int OFF_RING = RW * ROWBUF;    // in-warp rings of workers 1..RW-1, then the ring of worker 0
   static constexpr int OFF_RING0 = OFF_RING + (RW - 1) * kRingI * ENT;
@@ -123,7 +123,7 @@ struct SweepGeom {
   static constexpr int WARP_U4 = OFF_WTA + RW * WTA;
   static constexpr int STAGE_U4 = 1;               // the mbarrier of the TMA copies from the left CTA's entries
   static constexpr int NW_FIT = (kSmemMax - kFlagBytes - STAGE_U4 * 16) / (WARP_U4 * 16);
-  static constexpr int NW = NW_FIT > MAXNW ? MAXNW : NW_FIT;  // warps per CTA
+  static constexpr int NW = NW_FIT > kMaxNW ? kMaxNW : NW_FIT;  // warps per CTA
   static constexpr int SPC = NW * RW;             // strips per CTA task
   static constexpr size_t SMEM = (size_t)(NW * WARP_U4 + STAGE_U4) * 16 + kFlagBytes;
 };
@@ -231,9 +231,9 @@ __device__ __forceinline__ bool wait_cta(const int* flag, int need, volatile int
 // FULL: every lane of a worker holds disparities (D is LPP x 16), so the "lane without disparities" cases fold away
 // SMALL: four path costs of a pixel sum to less than 2^15 (4 x (largest block cost + P2) <= 32767, checked on the host), so a
 //        pass can add them with plain (three-input) adds and only the final S of pass 2 needs the saturation of A.5
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false, bool FULL = false, bool SMALL = false>
-__global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_sweep(const SweepArgs a) {
-  using G = SweepGeom<LPP, SECOND, MAXNW>;
+template <int LPP, int PATHS, bool SECOND, int K, bool WAY3 = false, bool FULL = false, bool SMALL = false>
+__global__ void __launch_bounds__(SweepGeom<LPP, SECOND, K>::NW * 32, 1) k_sweep(const SweepArgs a) {
+  using G = SweepGeom<LPP, SECOND, K>;
   constexpr int RW = G::RW, NV = G::NV, VEC = G::VEC, REC = G::REC, ENT = G::ENT, NW = G::NW;
   constexpr bool HAS_V = (PATHS & P_V) != 0, HAS_DL = (PATHS & P_DL) != 0, HAS_DR = (PATHS & P_DR) != 0;
   constexpr bool VERT = HAS_V || HAS_DL || HAS_DR;
@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
     if (task >= ntasks || *sAbort) break;
     const int frame = task % a.nframes, sg = task / a.nframes;
     const int sFirst = sg * G::SPC + warp * RW;  // strip of this warp's worker 0
-    auto y0of = [&](int s) { return max(0, s * kK - W1 + 1); };
-    auto y1of = [&](int s) { return min(H - 1, s * kK + kK - 1); };
+    auto y0of = [&](int s) { return max(0, s * K - W1 + 1); };
+    auto y1of = [&](int s) { return min(H - 1, s * K + K - 1); };
     if (lane == 0) { sProg[warp] = 0; sCons[warp] = y0of(sFirst); }
     __syncthreads();
     if (sFirst > a.smax) continue;  // whole warp beyond the last strip (still takes part in the barriers above)
@@ -333,12 +333,12 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
     // ---- per-task register state
     uint32_t Hs[kNR], Vd1[kNR], DLd1[kNR], DLd2[kNR];
     uint32_t mH = 0, mVd1 = 0, mDLd1 = 0, mDLd2 = 0;
-    uint32_t recM[kK][3];   // mins of the records in the row buffer
-    uint4 cb[kK][NV], sb[kK][NV];  // C (and S of pass 1) of this chunk, loaded one chunk ahead
+    uint32_t recM[K][3];   // mins of the records in the row buffer
+    uint4 cb[K][NV], sb[K][NV];  // C (and S of pass 1) of this chunk, loaded one chunk ahead
 #pragma unroll
     for (int q = 0; q < kNR; q++) Hs[q] = Vd1[q] = DLd1[q] = DLd2[q] = 0;
 #pragma unroll
-    for (int i = 0; i < kK; i++) {
+    for (int i = 0; i < K; i++) {
       recM[i][0] = recM[i][1] = recM[i][2] = 0;
 #pragma unroll
       for (int h = 0; h < NV; h++) cb[i][h] = sb[i][h] = make_uint4(0, 0, 0, 0);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       Tlast = T;
       const int r = T - j;                               // row of this worker
       const bool act = r >= y0 && r <= y1;
-      const int xl = s * kK - r;                         // leftmost column of the chunk
+      const int xl = s * K - r;                         // leftmost column of the chunk
       const bool act0 = T >= y0F && T <= y1F;            // worker 0 of the warp has a row
       const int rL = T - (RW - 1);
       const bool actL = rL >= y0L && rL <= y1L;          // worker RW-1 has a row (and a strip)
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       pfA += clock64() - pfA0;
       const long long pfB0 = clock64();
 #endif
-      // ================================================================== phase B: kK pixels
+      // ================================================================== phase B: K pixels
       // INTERIOR: every worker of the warp is on a row that is neither the first nor the last of its strip and all its pixels
       // (and the ones fetched for the next row) lie strictly inside the volume: no predecessor is outside, nothing is
       // predicated.  The test is warp-uniform arithmetic on T, so the warp takes one of two copies of the chunk code.
@@ -484,10 +484,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       // registers that are copied into cb / sb after the last pixel (a full row step of latency for every pixel's fetch;
       // 4 = the same for C only, S as in 0)
       constexpr bool EARLY_C = SV_SWEEP_LDPOS == 3 || SV_SWEEP_LDPOS == 4, EARLY_S = SECOND && SV_SWEEP_LDPOS == 3;
-      uint4 nbC[EARLY_C ? kK : 1][NV], nbS[EARLY_S ? kK : 1][NV];
+      uint4 nbC[EARLY_C ? K : 1][NV], nbS[EARLY_S ? K : 1][NV];
       if constexpr (EARLY_C) {
 #pragma unroll
-        for (int i = 0; i < kK; i++) {
+        for (int i = 0; i < K; i++) {
           const int xn = xl + i - 1;
           const bool ld = IN_LD || (actn && (unsigned)xn < (unsigned)W1);
           const unsigned off = ld ? offNext0 + (unsigned)(i * stepU4) : 0u;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         }
       }
 #pragma unroll
-      for (int i = 0; i < kK; i++) {
+      for (int i = 0; i < K; i++) {
         if (SV_SWEEP_PIXFENCE && i > 0) asm volatile("" ::: "memory");
         const int x = xl + i;
         const bool on = IN_ST || (act && (unsigned)x < (unsigned)W1);   // stores, selection output
@@ -614,10 +614,10 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
         }
         recM[i][0] = mV; recM[i][1] = mDL; recM[i][2] = mDR;
         // ---- hand-over to the right neighbour: the last two pixels of the chunk
-        if (i >= kK - 2) {
+        if (i >= K - 2) {
 #pragma unroll
           for (int h = 0; h < NV; h++) {
-            if (i == kK - 2) {
+            if (i == K - 2) {
               if (HAS_DL) eOut[3 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
             } else {
               eOut[0 * VEC + h * LPP] = make_uint4(Hs[4 * h], Hs[4 * h + 1], Hs[4 * h + 2], Hs[4 * h + 3]);
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
               if (HAS_DL) eOut[2 * VEC + h * LPP] = make_uint4(DLd2[4 * h], DLd2[4 * h + 1], DLd2[4 * h + 2], DLd2[4 * h + 3]);
             }
           }
-          if (i == kK - 1) eMins = make_uint4(mH, mV, mDL, mDLprev);
+          if (i == K - 1) eMins = make_uint4(mH, mV, mDL, mDLprev);
           mDLprev = mDL;
         }
         // ---- output of the pixel
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       }
       if constexpr (EARLY_C) {
 #pragma unroll
-        for (int i = 0; i < kK; i++)
+        for (int i = 0; i < K; i++)
 #pragma unroll
           for (int h = 0; h < NV; h++) {
             cb[i][h] = nbC[i][h];
@@ -687,8 +687,8 @@ __global__ void __launch_bounds__(SweepGeom<LPP, SECOND, MAXNW>::NW * 32, 1) k_s
       if (lane == 0 && actL && hasRight && !rightGlobal) st_flag(&sProg[warp], rL + 1);
           };
       {
-        const int xw = sFirst * kK - T;  // leftmost column of worker 0's chunk; worker j starts (kK + 1) j columns further right
-        const bool interior = T >= RW && T <= H - 2 && xw >= 1 && xw + (kK + 1) * (RW - 1) + kK - 1 <= W1 - 2;
+        const int xw = sFirst * K - T;  // leftmost column of worker 0's chunk; worker j starts (K + 1) j columns further right
+        const bool interior = T >= RW && T <= H - 2 && xw >= 1 && xw + (K + 1) * (RW - 1) + K - 1 <= W1 - 2;
         if constexpr ((SV_SWEEP_INTERIOR & 1) != 0) {
           if (interior) phaseB(std::true_type{});
           else phaseB(std::false_type{});
@@ -723,78 +723,180 @@ int lpp_of(int D) {
 
 template <int LPP>
 struct Dims {
-  static int spc(bool second, bool low) {
-    if (low) return second ? SweepGeom<LPP, true, kLowNW>::SPC : SweepGeom<LPP, false, kLowNW>::SPC;
+  static int spc(bool second, int k) {
+    if (k == kLowK) return second ? SweepGeom<LPP, true, kLowK>::SPC : SweepGeom<LPP, false, kLowK>::SPC;
     return second ? SweepGeom<LPP, true>::SPC : SweepGeom<LPP, false>::SPC;
   }
-  static int ent() { return SweepGeom<LPP, false>::ENT; }
 };
-int spc_of(int lpp, bool second, bool low) {
+int spc_of(int lpp, bool second, int k) {
   switch (lpp) {
-    case 1: return Dims<1>::spc(second, low);
-    case 2: return Dims<2>::spc(second, low);
-    case 4: return Dims<4>::spc(second, low);
-    case 8: return Dims<8>::spc(second, low);
-    default: return Dims<16>::spc(second, low);
+    case 1: return Dims<1>::spc(second, k);
+    case 2: return Dims<2>::spc(second, k);
+    case 4: return Dims<4>::spc(second, k);
+    case 8: return Dims<8>::spc(second, k);
+    default: return Dims<16>::spc(second, k);
   }
 }
 int ent_of(int lpp) { return 4 * lpp * (kNR / 4) + 1; }
-int smax_of(const SgbmCfg& cfg) { return (cfg.W1 - 1 + cfg.H - 1) / kK; }
-int groups_of(const SgbmCfg& cfg, bool second, bool low) {
-  const int spc = spc_of(lpp_of(cfg.D), second, low);
-  return (smax_of(cfg) + 1 + spc - 1) / spc;
+int smax_of(const SgbmCfg& cfg, int k) { return (cfg.W1 - 1 + cfg.H - 1) / k; }
+int groups_of(const SgbmCfg& cfg, bool second, int k) {
+  const int spc = spc_of(lpp_of(cfg.D), second, k);
+  return (smax_of(cfg, k) + 1 + spc - 1) / spc;
+}
+int max_groups(const SgbmCfg& cfg) {  // over both passes and both strip widths
+  int g = 1;
+  for (int k : {kLowK, kK}) g = std::max(g, std::max(groups_of(cfg, false, k), groups_of(cfg, true, k)));
+  return g;
+}
+// hand-over buffers of one pass over `nframes` frames
+size_t flag_ints(const SgbmCfg& cfg, int nframes) { return (size_t)nframes * max_groups(cfg) + 64; }
+size_t edge_u4(const SgbmCfg& cfg, int nframes) {
+  return (size_t)nframes * std::max(max_groups(cfg) - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D));
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3, bool FULL, bool SMALL = false>
+template <int LPP, int PATHS, bool SECOND, int K, bool WAY3, bool FULL, bool SMALL = false>
 cudaError_t launch_full(const SweepArgs& a, int grid, cudaStream_t st) {
-  using G = SweepGeom<LPP, SECOND, MAXNW>;
-  auto* k = k_sweep<LPP, PATHS, SECOND, MAXNW, WAY3, FULL, SMALL>;
+  using G = SweepGeom<LPP, SECOND, K>;
+  auto* k = k_sweep<LPP, PATHS, SECOND, K, WAY3, FULL, SMALL>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return e;
   k<<<grid, G::NW * 32, G::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int LPP, int PATHS, bool SECOND, int MAXNW, bool WAY3 = false>
+template <int LPP, int PATHS, bool SECOND, int K, bool WAY3 = false>
 cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
-  // the specialisation without idle lanes is built for the throughput kernels of the common modes only
-  if (a.nAct == LPP && MAXNW == kMaxNW && !WAY3) {
-    if (a.smallSums && PATHS == 15) return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true, true>(a, grid, st);
-    return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, true>(a, grid, st);
+  // the specialisations without idle lanes are built for the common modes only
+  if constexpr (!WAY3 && PATHS != P_H) {
+    if (a.nAct == LPP) {
+      if constexpr (PATHS == 15) {
+        if (a.smallSums) return launch_full<LPP, PATHS, SECOND, K, WAY3, true, true>(a, grid, st);
+      }
+      return launch_full<LPP, PATHS, SECOND, K, WAY3, true>(a, grid, st);
+    }
   }
-  return launch_full<LPP, PATHS, SECOND, MAXNW, WAY3, false>(a, grid, st);
+  return launch_full<LPP, PATHS, SECOND, K, WAY3, false>(a, grid, st);
 }
 
 template <int LPP, int PATHS, bool SECOND, bool WAY3 = false>
-cudaError_t launch_one(const SweepArgs& a, bool low, int grid, cudaStream_t st) {
-  return low ? launch_nw<LPP, PATHS, SECOND, kLowNW, WAY3>(a, grid, st) : launch_nw<LPP, PATHS, SECOND, kMaxNW, WAY3>(a, grid, st);
+cudaError_t launch_one(const SweepArgs& a, int k, int grid, cudaStream_t st) {
+  return k == kLowK ? launch_nw<LPP, PATHS, SECOND, kLowK, WAY3>(a, grid, st) : launch_nw<LPP, PATHS, SECOND, kK, WAY3>(a, grid, st);
 }
 
 template <int LPP>
-cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, bool low, bool way3, int grid, cudaStream_t st) {
-  if (way3 && second) return launch_one<LPP, P_H, true, true>(a, low, grid, st);   // MODE_SGBM_3WAY: backward path + its selection rule
+cudaError_t launch_lpp(const SweepArgs& a, int paths, bool second, int k, bool way3, int grid, cudaStream_t st) {
+  if (way3 && second) return launch_one<LPP, P_H, true, true>(a, k, grid, st);   // MODE_SGBM_3WAY: backward path + its selection rule
   if (!second) {
-    if (paths == 15) return launch_one<LPP, 15, false>(a, low, grid, st);
-    return launch_one<LPP, P_H | P_V, false>(a, low, grid, st);
+    if (paths == 15) return launch_one<LPP, 15, false>(a, k, grid, st);
+    if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, false>(a, k, grid, st);
+    return launch_one<LPP, P_H, false>(a, k, grid, st);   // backward pass of MODE_SGBM when the passes run side by side
   }
-  if (paths == 15) return launch_one<LPP, 15, true>(a, low, grid, st);
-  if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, true>(a, low, grid, st);
-  return launch_one<LPP, P_H, true>(a, low, grid, st);
+  if (paths == 15) return launch_one<LPP, 15, true>(a, k, grid, st);
+  if (paths == (P_H | P_V)) return launch_one<LPP, P_H | P_V, true>(a, k, grid, st);
+  return launch_one<LPP, P_H, true>(a, k, grid, st);
+}
+
+cudaError_t launch_sweep(const SweepArgs& a, int lpp, int paths, bool second, int k, bool way3, int grid, cudaStream_t st) {
+#if defined(SV_SWEEP_ONLY8)   // quick experiment builds: only the D = 128 MODE_HH throughput kernels are instantiated
+  if (lpp != 8 || paths != 15 || k != kK || way3) return cudaErrorNotSupported;
+  return second ? launch_nw<8, 15, true, kK>(a, grid, st) : launch_nw<8, 15, false, kK>(a, grid, st);
+#else
+  switch (lpp) {
+    case 1: return launch_lpp<1>(a, paths, second, k, way3, grid, st);
+    case 2: return launch_lpp<2>(a, paths, second, k, way3, grid, st);
+    case 4: return launch_lpp<4>(a, paths, second, k, way3, grid, st);
+    case 8: return launch_lpp<8>(a, paths, second, k, way3, grid, st);
+    default: return launch_lpp<16>(a, paths, second, k, way3, grid, st);
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Winner-take-all over S = S1 + S2 when the two passes ran side by side (each as a "first" pass that stores the sum of its
+// paths): the saturating add of A.5 and sweep_wta, one pixel per worker.  HBM-bound: 4 B per volume cell.
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__global__ void __launch_bounds__(256) k_wta_sum(const uint4* __restrict__ S1, const uint4* __restrict__ S2, uint2* __restrict__ sel,
+                                                 long long npix, long long framePix, unsigned frameU4, int pixU4, int D, int nAct,
+                                                 int uniqF, uint32_t uniqMagic) {
+  constexpr int RW = 32 / LPP, NV = kNR / 4, VEC = LPP * NV;
+  __shared__ uint4 sW[8 * RW * VEC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane / LPP, gl = lane % LPP;
+  const bool active = gl < nAct;
+  uint16_t* wta = (uint16_t*)(sW + (warp * RW + j) * VEC);
+  const long long stride = (long long)gridDim.x * 8 * RW;
+  for (long long p0 = ((long long)blockIdx.x * 8 + warp) * RW; p0 < npix; p0 += stride) {   // warp-uniform bounds
+    const long long p = p0 + j;
+    const bool on = p < npix;
+    uint32_t s[kNR];
+#pragma unroll
+    for (int q = 0; q < kNR; q++) s[q] = 0;
+    if (on && active) {
+      const long long f = p / framePix, rem = p - f * framePix;
+      const size_t off = (size_t)f * frameU4 + (size_t)rem * pixU4 + gl * NV;
+#pragma unroll
+      for (int h = 0; h < NV; h++) {
+        const uint4 u = __ldcs(S1 + off + h), v = __ldcs(S2 + off + h);
+        s[4 * h] = __viaddmin_u16x2(u.x, v.x, kMax2); s[4 * h + 1] = __viaddmin_u16x2(u.y, v.y, kMax2);
+        s[4 * h + 2] = __viaddmin_u16x2(u.z, v.z, kMax2); s[4 * h + 3] = __viaddmin_u16x2(u.w, v.w, kMax2);
+      }
+    }
+    uint2 o;
+    sweep_wta<LPP, false>(s, wta, gl, active, lane, D, uniqF, uniqMagic, o);
+    if (on && gl == 0) sel[p] = o;
+  }
+}
+template <int LPP>
+cudaError_t launch_wta_sum(const SweepArgs& a, const uint4* S2, int numSM, cudaStream_t st) {
+  const long long framePix = (long long)a.H * a.W1, npix = framePix * a.nframes;
+  const long long perBlock = 8 * (32 / LPP);
+  const int grid = (int)std::min<long long>((npix + perBlock - 1) / perBlock, (long long)numSM * 32);
+  k_wta_sum<LPP><<<grid, 256, 0, st>>>(a.S, S2, a.sel, npix, framePix, a.frameU4, a.pixU4, a.D, a.nAct, a.uniqF, a.uniqMagic);
+  return cudaGetLastError();
+}
+
+int env_int(const char* name) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : -1;
 }
 
 }  // namespace
 
+// S volumes of `nframes` pairs: up to kSplitFrames pairs per call run the two passes side by side, each into its own volume
+// Up to this many pairs per call run the two passes side by side (see sgbm_aggregate_sweep).  Measured at 1080p / 128 on 148 SMs
+// (24 strip groups per pair and pass): side by side wins up to 16 pairs per call (6.4 instead of 10.3 ms at 4, 17.3 instead of
+// 17.8 ms at 16); beyond that the extra 4 B per cell of the separate selection cost more than the fuller machine gains.
+// SVGPU_SPLIT_FRAMES overrides the limit (experiments).
+static int split_limit(const SgbmCfg& cfg, int numSM) {
+  const int v = env_int("SVGPU_SPLIT_FRAMES");
+  if (v >= 0) return v;
+  if (cfg.W1 <= 0 || cfg.mode == SV_MODE_SGBM_3WAY) return 0;
+  return (int)(5ll * numSM / (2ll * groups_of(cfg, false, kK)));
+}
+static int num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+size_t sgbm_s_frames(const SgbmCfg& cfg, int nframes) { return nframes <= split_limit(cfg, num_sms()) ? 2 * (size_t)nframes : (size_t)nframes; }
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
-  return ((size_t)nframes * std::max(groups_of(cfg, false, true), groups_of(cfg, true, true)) + 64) * sizeof(int);
+  return 2 * flag_ints(cfg, nframes) * sizeof(int);
 }
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
   if (cfg.W1 <= 0) return 256;
-  const int g = std::max(groups_of(cfg, false, true), groups_of(cfg, true, true));  // the low-latency variant has the most groups
-  return (size_t)nframes * std::max(g - 1, 1) * (size_t)cfg.H * ent_of(lpp_of(cfg.D)) * sizeof(uint4);
+  return edge_u4(cfg, (int)sgbm_s_frames(cfg, nframes)) * sizeof(uint4);
 }
 
 // Aggregation + selection of `nframes` pairs: S scratch and `sel` are produced; C is read twice.
+//
+// Throughput (many pairs per call): two launches on `st`, the second carries its four paths, adds the first pass's S and selects
+// in registers (8 B per cell).  Few pairs per call: the machine is not full and a call takes as long as its wavefronts —
+// H + (W1 + H) / K row steps per pass.  The second pass does not depend on the first until the sums meet, so the two passes
+// then run side by side — on `st` and on sc.aux, each storing the sum of its paths — and k_wta_sum adds and selects
+// (min(min(a, M) + min(b, M), M) = min(a + b, M): the saturation of the fused form).  When the tasks of both passes fit on
+// the SMs at once (1-3 pairs at 1080p) the strips are 2 columns wide, which shortens the wavefront further.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats, int cn) {
   int dev = 0, numSM = 0;
@@ -803,14 +905,11 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   if (e0 != cudaSuccess) return e0;
   SweepArgs a{};
   a.C = (const uint4*)sc.C; a.S = (uint4*)sc.S; a.sel = (uint2*)sc.sel;
-  a.edges = (uint4*)sc.edges;
-  a.ticket = (int*)sc.flags;
-  a.gprog = (int*)sc.flags + 64;
   a.status = sc.status;
   a.W1 = cfg.W1; a.H = cfg.H; a.D = cfg.D; a.nAct = cfg.D / kDPL;
   // largest block cost of single-channel input: blockSize^2 x (2 ftzero + 63); every path cost is <= that + P2 (A.5)
   a.smallSums = cn <= 1 && 4ll * ((2 * cfg.r + 1) * (2 * cfg.r + 1) * (2 * cfg.ftzero + 63) + cfg.P2) <= 32767;
-  a.nframes = nframes; a.smax = smax_of(cfg); a.debugS = debugS;
+  a.nframes = nframes; a.debugS = debugS;
   a.frameU4 = (unsigned)(sc.frameCells / 8);
   a.pixU4 = cfg.D / 8;
   a.rowU4 = (unsigned)cfg.W1 * (unsigned)a.pixU4;
@@ -821,34 +920,66 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   a.uniqF = 100 - cfg.uniq;
   a.uniqMagic = a.uniqF >= 2 ? (uint32_t)((0x100000000ull + a.uniqF - 1) / a.uniqF) : 0u;
   // MODE_SGBM_3WAY (on stripe frames, see sgbm.cu): left-to-right + top-down in pass 1, right-to-left in pass 2
-  const int pass1 = (cfg.mode == SV_MODE_HH4 || cfg.mode == SV_MODE_SGBM_3WAY) ? (P_H | P_V) : 15;
+  const bool way3 = cfg.mode == SV_MODE_SGBM_3WAY;
+  const int pass1 = (cfg.mode == SV_MODE_HH4 || way3) ? (P_H | P_V) : 15;
   const int pass2 = cfg.mode == SV_MODE_HH ? 15 : (cfg.mode == SV_MODE_HH4 ? (P_H | P_V) : P_H);
   const int lpp = lpp_of(cfg.D);
-  // SVGPU_SWEEP_NW=4|8 pins the variant (tests run every case through both)
-  const char* ev = std::getenv("SVGPU_SWEEP_NW");
-  const int forceNW = ev ? std::atoi(ev) : 0;
+  // SVGPU_SWEEP_K=2|4 and SVGPU_SWEEP_SPLIT=0|1 pin the variant (the tests run every case through all of them)
+  const int forceK = env_int("SVGPU_SWEEP_K"), forceSplit = env_int("SVGPU_SWEEP_SPLIT");
+  const size_t fInts = flag_ints(cfg, nframes), eU4 = edge_u4(cfg, nframes);
+  const bool canSplit = !way3 && !debugS && sc.aux && sc.evFork && sc.evJoin && forceSplit != 0 &&
+                        sc.sBytes >= 2 * (size_t)nframes * sc.frameCells * 2 && sc.flagBytes >= 2 * fInts * sizeof(int) &&
+                        sc.edgeBytes >= 2 * eU4 * sizeof(uint4);
+  int K = kK;
+  bool split = false;
+#if !defined(SV_SWEEP_ONLY8)
+  if (canSplit && 2ll * nframes * groups_of(cfg, false, kLowK) <= numSM) { split = true; K = kLowK; }
+  else if (canSplit && nframes <= split_limit(cfg, numSM)) split = true;
+  // passes one after the other, measured at 1080p / 128: 2-column strips win up to 8 pairs per call (192 tasks of the 4-column
+  // build), 4-column strips from 12
+  else if (2ll * nframes * groups_of(cfg, true, kK) <= 3ll * numSM) K = kLowK;
+  if (forceK == kLowK || forceK == kK) K = forceK;
+  if (canSplit && forceSplit == 1) split = true;
+#endif
+  a.smax = smax_of(cfg, K);
+  if (split) {
+    a.G = groups_of(cfg, false, K);
+    const int grid = std::min(nframes * a.G, numSM);
+    cudaError_t e = cudaMemsetAsync(sc.flags, 0, 2 * fInts * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaEventRecord(sc.evFork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sc.aux, sc.evFork, 0);
+    if (e != cudaSuccess) return e;
+    SweepArgs b = a;
+    a.ticket = (int*)sc.flags; a.gprog = a.ticket + 64; a.edges = (uint4*)sc.edges; a.flip = 0;
+    b.ticket = (int*)sc.flags + fInts; b.gprog = b.ticket + 64; b.edges = (uint4*)sc.edges + eU4; b.flip = 1;
+    b.S = a.S + (size_t)nframes * a.frameU4;
+    e = launch_sweep(a, lpp, pass1, false, K, false, grid, st);
+    if (e == cudaSuccess) e = launch_sweep(b, lpp, pass2, false, K, false, grid, sc.aux);
+    // the join is recorded even when a launch failed, so that `st` never waits for an event of an earlier call
+    cudaError_t e2 = cudaEventRecord(sc.evJoin, sc.aux);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, sc.evJoin, 0);
+    if (e != cudaSuccess) return e;
+    if (e2 != cudaSuccess) return e2;
+    switch (lpp) {
+      case 1: e = launch_wta_sum<1>(a, b.S, numSM, st); break;
+      case 2: e = launch_wta_sum<2>(a, b.S, numSM, st); break;
+      case 4: e = launch_wta_sum<4>(a, b.S, numSM, st); break;
+      case 8: e = launch_wta_sum<8>(a, b.S, numSM, st); break;
+      default: e = launch_wta_sum<16>(a, b.S, numSM, st); break;
+    }
+    if (stats) stats->launches += 3;
+    return e;
+  }
+  a.edges = (uint4*)sc.edges;
+  a.ticket = (int*)sc.flags;
+  a.gprog = (int*)sc.flags + 64;
   for (int pass = 0; pass < 2; pass++) {
-    // a few pairs per call: half as many warps per CTA give every warp its own scheduler and put twice as many SMs to work
-    bool low = (long long)nframes * groups_of(cfg, pass == 1, true) <= numSM;
-    if (forceNW) low = forceNW == kLowNW;
-    a.G = groups_of(cfg, pass == 1, low);
+    a.G = groups_of(cfg, pass == 1, K);
     cudaError_t e = cudaMemsetAsync(sc.flags, 0, ((size_t)nframes * a.G + 64) * sizeof(int), st);
     if (e != cudaSuccess) return e;
     a.flip = pass;
-    const int paths = pass ? pass2 : pass1;
     const int grid = std::min(nframes * a.G, numSM);
-#if defined(SV_SWEEP_ONLY8)   // quick experiment builds: only the D = 128 MODE_HH throughput kernels are instantiated
-    if (lpp != 8 || paths != 15 || low) return cudaErrorNotSupported;
-    e = pass == 0 ? launch_nw<8, 15, false, kMaxNW>(a, grid, st) : launch_nw<8, 15, true, kMaxNW>(a, grid, st);
-#else
-    switch (lpp) {
-      case 1: e = launch_lpp<1>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
-      case 2: e = launch_lpp<2>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
-      case 4: e = launch_lpp<4>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
-      case 8: e = launch_lpp<8>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
-      default: e = launch_lpp<16>(a, paths, pass == 1, low, cfg.mode == SV_MODE_SGBM_3WAY, grid, st); break;
-    }
-#endif
+    e = launch_sweep(a, lpp, pass ? pass2 : pass1, pass == 1, K, way3, grid, st);
     if (stats) stats->launches++;
     if (e != cudaSuccess) return e;
   }
