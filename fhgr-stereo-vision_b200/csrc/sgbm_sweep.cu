@@ -9,13 +9,14 @@
 // reads C and S, adds its 4 paths and selects the winner in registers: 8 B per volume cell in total.
 //
 // Work decomposition (per pass, in sweep coordinates; pass 2 is pass 1 on the volume flipped in x and y):
-//   * the image is cut into strips of kK columns whose borders move one pixel to the left per row:
-//     strip s covers columns [s*kK - y, s*kK - y + kK) of row y.  With that skew every predecessor of a
+//   * the image is cut into strips of K columns (4; 2 when a call has so few pairs that its wavefronts set its
+//     duration) whose borders move one pixel to the left per row:
+//     strip s covers columns [s*K - y, s*K - y + K) of row y.  With that skew every predecessor of a
 //     pixel — (x-1,y), (x-1,y-1), (x,y-1), (x+1,y-1) — lies in the same strip or in the strip to the LEFT,
 //     so strips form a one-directional pipeline;
 //   * a "worker" is a group of LPP lanes (16 disparities per lane) that owns one strip and walks it top to
-//     bottom, kK pixels per row ("chunk").  The horizontal path lives in registers; the three paths that
-//     come from the row above live in a lane-private shared-memory row buffer (kK records);
+//     bottom, K pixels per row ("chunk").  The horizontal path lives in registers; the three paths that
+//     come from the row above live in a lane-private shared-memory row buffer (K records);
 //   * per chunk a worker receives from its left neighbour the horizontal path of the pixel left of the
 //     chunk and the vertical/diagonal paths of the two pixels above-left of it, and hands the same to its
 //     right neighbour: one small "entry" per row instead of one hand-over per pixel;
@@ -26,6 +27,8 @@
 //   * CTAs are persistent and draw (frame, strip group) tasks from a ticket counter, strip groups in
 //     ascending order.  A task only waits for the task to its left, which has a smaller ticket and is
 //     therefore resident or finished: no deadlock whatever the residency.
+//   * few pairs per call: the two passes run side by side on two streams as two "first" passes (the second on the flipped
+//     volume into its own S) and k_wta_sum adds and selects — see sgbm_aggregate_sweep.
 //
 // Volume layout: [frame][y][x'][D] uint16, the D costs of a pixel in groups of 16 with the two halves of a
 // group interleaved (word i of a group = disparities d0+i and d0+i+8), so that the d-1 / d+1 neighbours of
