@@ -120,8 +120,10 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   const size_t w1 = g.W1 > 0 ? g.W1 : 0;
   // + 256: the TMA staging of the cost kernel copies whole 16-byte units and may read one operand word past a row
   const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2) + 256;
+  // S holds one volume per pair, two when the passes of a few pairs run side by side, one per path for single small pairs
+  const size_t sFrames = way3 ? (size_t)batch : std::max(sgbm_s_frames(gs, batch), sgbm_lines_frames(gs, std::min(batch, sgbm_lines_max_frames(gs, cells))));
   const size_t need[svgpu_ctx::kScratchBufs] = {
-      planeBytes, planeBytes, (size_t)batch * cells * 2, (way3 ? (size_t)batch : sgbm_s_frames(gs, batch)) * cells * 2, (size_t)batch * vrows * w1 * 8,
+      planeBytes, planeBytes, (size_t)batch * cells * 2, sFrames * cells * 2, (size_t)batch * vrows * w1 * 8,
       (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2, 256, sgbm_flags_bytes(gs, sweepFrames), sgbm_edges_bytes(gs, sweepFrames)};
   bool fits = c->sc.dispRaw != nullptr;
   for (int i = 0; i < svgpu_ctx::kScratchBufs; i++) fits = fits && c->allocBytes[i] >= need[i];

@@ -99,6 +99,11 @@ cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& view, int nfram
 // sgbm_sweep.cu: path aggregation + winner-take-all as two fused sweeps over skewed column strips
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats, int cn = 1);
+// sgbm_lines.cu: aggregation of single pairs, one worker per line and direction
+int sgbm_lines_max_frames(const SgbmCfg& cfg, size_t frameCells);   // pairs per call up to which the line form is used
+bool sgbm_lines_ok(const SgbmCfg& cfg, int nframes, size_t frameCells);
+size_t sgbm_lines_frames(const SgbmCfg& cfg, int nframes);   // path volumes it needs in S
+cudaError_t sgbm_aggregate_lines(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, cudaStream_t st, LaunchStats* stats);
 size_t sgbm_s_frames(const SgbmCfg& cfg, int nframes);   // S volumes that `nframes` pairs per call need
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes);
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes);

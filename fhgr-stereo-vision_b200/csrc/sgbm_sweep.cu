@@ -902,6 +902,9 @@ size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
 // the SMs at once (1-3 pairs at 1080p) the strips are 2 columns wide, which shortens the wavefront further.
 cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int nframes, int debugS, cudaStream_t st,
                                  LaunchStats* stats, int cn) {
+  // a single small pair: one worker per line and direction instead of the strip pipeline (sgbm_lines.cu)
+  if (!debugS && sgbm_lines_ok(cfg, nframes, sc.frameCells) && sc.sBytes >= sgbm_lines_frames(cfg, nframes) * sc.frameCells * 2)
+    return sgbm_aggregate_lines(cfg, sc, nframes, st, stats);
   int dev = 0, numSM = 0;
   cudaError_t e0 = cudaGetDevice(&dev);
   if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);

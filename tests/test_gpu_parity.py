@@ -352,16 +352,18 @@ def test_cpp_facade_matches_python_pipeline(svgpu, oracle, tmp_path):
         assert np.allclose(np.array(got[key].split(), np.float32), want, rtol=1e-6, atol=0), (key, got[key], want)
 
 
-@pytest.mark.parametrize("sweep_k,sweep_split", [("4", "0"), ("2", "0"), ("2", "1"), ("4", "1")])
-def test_sgbm_random_configs_bit_exact(svgpu, oracle, sweep_k, sweep_split, monkeypatch):
+@pytest.mark.parametrize("sweep_k,sweep_split,lines", [("4", "0", "0"), ("2", "0", "0"), ("2", "1", "0"), ("4", "1", "0"), ("4", "0", "1")])
+def test_sgbm_random_configs_bit_exact(svgpu, oracle, sweep_k, sweep_split, lines, monkeypatch):
     """Seeded random sweep over image sizes (incl. fewer computed columns than one strip and single-row images),
     disparity ranges, block sizes, penalties, uniqueness ratios, minDisparity signs and all three modes, on textured
     and on saturating noise inputs: bit-exact against the oracle.  Run once per variant of the aggregation: strips of 4 columns
     (throughput) and of 2 (which the library picks by itself for a few pairs per call), the two passes one after the other
-    (the second selects in registers) and side by side on two streams (k_wta_sum adds the two sums and selects)."""
+    (the second selects in registers) and side by side on two streams (k_wta_sum adds the two sums and selects), and the
+    line form of single small pairs (sgbm_lines.cu: one worker per line and direction)."""
     from svgpu.synth import synth_pair
     monkeypatch.setenv("SVGPU_SWEEP_K", sweep_k)
     monkeypatch.setenv("SVGPU_SWEEP_SPLIT", sweep_split)
+    monkeypatch.setenv("SVGPU_SWEEP_LINES", lines)
     rng = np.random.default_rng(20261018)
     bad = []
     for case in range(48):

@@ -42,6 +42,25 @@ if __name__ == "__main__":
             for B in ((1, 2, 4, 8, 16, 32) if W < 3840 else (1, 2, 4, 8)):
                 fps, _ = sgbm(W, H, D, mode, B)
                 print(f"{name}: {B} pair(s) per call: {B / fps * 1e3:7.2f} ms per call, {fps:7.1f} fps", flush=True)
+        # the whole chain for one pair per call with host buffers, wall clock: what one AnalyzeAndAnnotateImage call costs
+        from bench import big_calib, to_bgr
+        ALL = (svgpu.STAGE_REMAP | svgpu.STAGE_PREFILTER | svgpu.STAGE_SGBM | svgpu.STAGE_POSTFILTER | svgpu.STAGE_REPROJECT | svgpu.STAGE_DEPTH)
+        for (W, H, D, mode, name) in [(640, 480, 224, 3, "reference 640x480 D=224 HH4"), (1920, 1080, 128, 1, "config 3 1920x1080 D=128 HH")]:
+            l, r = synth_pair(H, W, D, seed=1)
+            l, r = to_bgr(l[None])[0], to_bgr(r[None])[0]
+            K, dd, P, Q = big_calib(W, H)
+            with svgpu.Context(W, H) as ctx:
+                ctx.set_sgbm(numDisparities=D, mode=mode, **dict(REF, speckleWindowSize=200, speckleRange=2))
+                for side in (0, 1):
+                    ctx.init_rectify_maps(side, K, dd, np.eye(3), P)
+                ctx.set_Q(Q); ctx.set_depth_consts(75.3, float(K[0, 0]))
+                for _ in range(3):
+                    ctx.pipeline(l, r, ALL, want_xyz=True, want_depth=True)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    ctx.pipeline(l, r, ALL, want_xyz=True, want_depth=True)
+                ms = (time.perf_counter() - t0) / 20 * 1e3
+            print(f"{name}: full chain (BGR in; disparity + XYZ + depth out), one pair per call, host buffers, wall clock: {ms:7.2f} ms per call", flush=True)
         sys.exit(0)
     fps, mpd = sgbm(1280, 720, 64, 0, 64); print(f"config 2  SGBM MODE_SGBM 1280x720 D=64, 64 pairs/step: {fps:8.1f} fps {mpd:10.0f} Mpix*disp/s")
     fps, mpd = sgbm(1280, 720, 64, 1, 64); print(f"          SGBM MODE_HH   1280x720 D=64, 64 pairs/step: {fps:8.1f} fps {mpd:10.0f} Mpix*disp/s")

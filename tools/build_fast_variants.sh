@@ -18,7 +18,7 @@ done
 wait
 for spec in "$@"; do
   tag="${spec%%:*}"; out="../../build/variants/$tag"
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libsvgpu.so" api.o sgbm.o "$out/sgbm_cost.o" "$out/sgbm_sweep.o" image_ops.o front_fused.o bm.o rectify.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libsvgpu.so" api.o sgbm.o "$out/sgbm_cost.o" "$out/sgbm_sweep.o" sgbm_lines.o image_ops.o front_fused.o bm.o rectify.o
   if [ -z "$KEEP_OBJ" ]; then rm -f "$out/sgbm_cost.o" "$out/sgbm_sweep.o"; fi   # the snapshot sent to the GPU box is limited to 512 MiB
   echo "built $out/libsvgpu.so"
 done

@@ -12,6 +12,6 @@ done
 wait
 for spec in "$@"; do
   tag="${spec%%:*}"; out="../../build/variants/$tag"
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libsvgpu.so" api.o sgbm.o sgbm_cost.o "$out/sgbm_sweep.o" image_ops.o front_fused.o bm.o rectify.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libsvgpu.so" api.o sgbm.o sgbm_cost.o "$out/sgbm_sweep.o" sgbm_lines.o image_ops.o front_fused.o bm.o rectify.o
   echo "built $out/libsvgpu.so"
 done
