@@ -455,6 +455,13 @@ def main():
     e2e_steps = args.steps if kind == "stream" else max(3, min(args.steps, 10))
     ms_e2e = timed(step_host, e2e_steps, 2, streaming=(kind != "bm"))
 
+    # one pair per call, the way the reference's front-ends call the library (device-resident, CUDA events; every rank runs it,
+    # rank 0's is reported): small calls take the latency forms of the aggregation
+    single_ms = None
+    if kind in ("sgbm", "stream"):
+        one = lambda i: ctx.sgbm_batch(Ld[:1], Rd[:1], out=out[:1])
+        single_ms = timed(one, 10, 3) / 10
+
     stats = gather_stats([ms, ms_e2e, float(B * dev_steps), float(csum % (1 << 40)), float(psum % (1 << 24)), float((psum >> 24) % (1 << 24))],
                          device=dev if world > 1 else None)
     ms_max, ms_e2e_max = float(stats[:, 0].max()), float(stats[:, 1].max())
@@ -480,6 +487,8 @@ def main():
                         "steps": e2e_steps, "fps": (B * world * e2e_steps) / (ms_e2e_max / 1e3), "frames": int(B * world * e2e_steps),
                         "api": {"pipeline": "svgpu_pipeline_enqueue_batch + svgpu_sync", "bm": "svgpu_bm_compute with host buffers"}.get(
                             kind, "svgpu_sgbm_enqueue_batch + svgpu_sync") + " on pinned host buffers (copy-in / kernels / copy-out of consecutive steps overlap)"}}
+        if single_ms is not None:
+            line["details"]["single_pair_call_ms"] = single_ms
         if kind == "stream":
             line["details"]["note"] = value_note
         if stage is not None:
