@@ -394,7 +394,7 @@ cudaError_t launch_cost(const SgbmCfg& cfg, const CostView& v, int nframes, cuda
   int bands = 1, rowsPerBand = (v.rowsOut + RB - 1) / RB * RB;
   {
     long long best = -1;
-    const int maxBands = std::max(1, std::min(16, (v.rowsOut + 63) / 64));
+    const int maxBands = std::max(1, std::min(64, v.rowsOut / 8));   // a single small pair is cut into enough bands to reach every SM
     for (int b = 1; b <= maxBands; b++) {
       const int rpb = ((v.rowsOut + b - 1) / b + RB - 1) / RB * RB;
       const int nb = (v.rowsOut + rpb - 1) / rpb;
