@@ -29,10 +29,12 @@ constexpr int kMaxDirs = 8;
 #define SV_LINES_L2AHEAD 8
 #endif
 // Pixels of C ahead of the walk: kPF in registers (covers an L2 hit) and a prefetch into L2 kL2Ahead pixels ahead (covers the
-// DRAM round trip).  Measured (profiles/r02_summary.md): the L2 prefetch gains 15-30 %, 8 ahead is as good as 16 and beats 32; a
-// deeper register ring gains nothing (a warp's outstanding loads share six scoreboards, so waiting for the oldest also waits
-// for younger ones); a cp.async ring in shared memory (4-16 pixels deep), 256-byte L2 fetch granules, burst prefetches,
-// prefetch.global.L1 and volatile-asm loads are all equal or slower.  What did gain: no branch inside the unrolled body.
+// DRAM round trip).  Measured (profiles/r02_summary.md): the L2 prefetch gains 15-30 %, 8 ahead is as good as 16 and beats 32.
+// A deeper register ring gained nothing while the unrolled body held a branch: the SASS then carried the ring through copies
+// placed right behind the loads, so every step waited for its newest load.  Without the branch the loads of an iteration are
+// issued as one batch into the registers they are read from (-12 % at 720p / 64 and 640 x 480 / 224).  A cp.async ring in shared
+// memory (4-16 pixels deep), 256-byte L2 fetch granules, burst prefetches, prefetch.global.L1 and volatile-asm loads were all
+// equal or slower.
 constexpr int kPF = SV_LINES_PF;
 constexpr int kL2Ahead = SV_LINES_L2AHEAD;
 
