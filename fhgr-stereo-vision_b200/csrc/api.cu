@@ -157,7 +157,10 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
 // A.1 parameter normalisation + the contract checks of this implementation
 int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
   if (p.numDisparities <= 0 || p.numDisparities % 16 != 0) return fail(c, SV_INVALID_SETTINGS, "numDisparities must be a positive multiple of 16");
-  if (p.numDisparities > 256) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported");
+  // up to 256 disparities every form of the aggregation is built; up to 512 the line form (a full warp per pixel) serves all
+  // call sizes.  MODE_SGBM_3WAY has its own driver around the strip pipeline and stays within 256.
+  if (p.numDisparities > 512) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 512 is not supported");
+  if (p.numDisparities > 256 && p.mode == SV_MODE_SGBM_3WAY) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported in MODE_SGBM_3WAY");
   if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4 && p.mode != SV_MODE_SGBM_3WAY)
     return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH, MODE_SGBM_3WAY or MODE_HH4");
   // 15 x 15 is the largest block whose cost fits 16 bits at all (225 x 93 + P2, checked below)

@@ -442,6 +442,15 @@ cudaError_t launch_cost_pair(const SgbmCfg& cfg, const CostView& sc, int nframes
 // Ctrue of `nframes` pairs from their pre-filter planes
 cudaError_t sgbm_cost_volume(const SgbmCfg& cfg, const CostView& sc, int nframes, int cn, cudaStream_t st) {
   // records staged per thread and row = (CH NC + CH NJ) / threads, CH = 2 planes per colour channel
+  if (cfg.D > 256) {
+    // 272 .. 512 disparities: 17 .. 32 disparity groups leave a 512-thread CTA 16 columns per tile (general builds, not tuned)
+    if (cfg.r >= 6) {
+      if (cn != 1 || cfg.r > 7) return cudaErrorInvalidConfiguration;
+      return cfg.r == 6 ? launch_cost<6, 16, 1, 2, 3, 2, true, 512>(cfg, sc, nframes, st) : launch_cost<7, 16, 1, 2, 3, 2, true, 512>(cfg, sc, nframes, st);
+    }
+    if (cn == 3) return launch_cost_r<16, 1, 4, 7, 6>(cfg, sc, nframes, st);
+    return launch_cost_r<16, 1, 8, 3>(cfg, sc, nframes, st);
+  }
   if (cfg.r >= 6) {
     // blockSize 13 / 15 (the 16-bit cost contract admits nothing larger, and single-channel input only): the general build with
     // its 13- / 15-row ring in shared memory and a two-row horizontal block

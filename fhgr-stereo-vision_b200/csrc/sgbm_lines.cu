@@ -200,6 +200,7 @@ int ndirs_of(int mode) { return mode == SV_MODE_HH ? 8 : mode == SV_MODE_HH4 ? 4
 // SVGPU_SWEEP_LINES=0|1 pins the choice (tests).
 int sgbm_lines_max_frames(const SgbmCfg& cfg, size_t frameCells) {
   if (cfg.W1 <= 0 || cfg.mode == SV_MODE_SGBM_3WAY || frameCells == 0) return 0;
+  if (cfg.D > 256) return 1;   // the only form built for more than 16 lanes per pixel: a call is served pair by pair
   const double perFrame = (double)frameCells * 2.0 * 3.0 * ndirs_of(cfg.mode);   // bytes moved per pair
   const char* f = std::getenv("SVGPU_SWEEP_LINES");
   if (f && f[0] == '0') return 0;
@@ -241,15 +242,26 @@ cudaError_t sgbm_aggregate_lines(const SgbmCfg& cfg, const SgbmScratch& sc, int 
     const int n = a.dy[k] == 0 ? cfg.H : a.dx[k] == 0 ? cfg.W1 : cfg.W1 + cfg.H - 1;
     a.lineBase[k + 1] = a.lineBase[k] + n;
   }
-  cudaError_t e;
-  switch (cfg.D / kDPL <= 1 ? 1 : cfg.D / kDPL <= 2 ? 2 : cfg.D / kDPL <= 4 ? 4 : cfg.D / kDPL <= 8 ? 8 : 16) {
-    case 1: e = launch_lines<1>(a, numSM, st); break;
-    case 2: e = launch_lines<2>(a, numSM, st); break;
-    case 4: e = launch_lines<4>(a, numSM, st); break;
-    case 8: e = launch_lines<8>(a, numSM, st); break;
-    default: e = launch_lines<16>(a, numSM, st); break;
+  const int groups = cfg.D / kDPL;
+  const int lpp = groups <= 1 ? 1 : groups <= 2 ? 2 : groups <= 4 ? 4 : groups <= 8 ? 8 : groups <= 16 ? 16 : 32;
+  // more pairs than the path volumes in S hold (numDisparities > 256: always one): pair by pair on the same volumes
+  const int per = std::max(1, std::min(nframes, sgbm_lines_max_frames(cfg, sc.frameCells)));
+  cudaError_t e = cudaSuccess;
+  for (int f0 = 0; f0 < nframes && e == cudaSuccess; f0 += per) {
+    a.nframes = std::min(per, nframes - f0);
+    a.dirU4 = (size_t)a.nframes * a.frameU4;
+    a.C = (const uint4*)sc.C + (size_t)f0 * a.frameU4;
+    a.sel = (uint2*)sc.sel + (size_t)f0 * cfg.H * cfg.W1;
+    switch (lpp) {
+      case 1: e = launch_lines<1>(a, numSM, st); break;
+      case 2: e = launch_lines<2>(a, numSM, st); break;
+      case 4: e = launch_lines<4>(a, numSM, st); break;
+      case 8: e = launch_lines<8>(a, numSM, st); break;
+      case 16: e = launch_lines<16>(a, numSM, st); break;
+      default: e = launch_lines<32>(a, numSM, st); break;
+    }
+    if (stats) stats->launches += 2;
   }
-  if (stats) stats->launches += 2;
   return e;
 }
 

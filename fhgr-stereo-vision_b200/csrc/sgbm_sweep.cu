@@ -874,7 +874,7 @@ int env_int(const char* name) {
 static int split_limit(const SgbmCfg& cfg, int numSM) {
   const int v = env_int("SVGPU_SPLIT_FRAMES");
   if (v >= 0) return v;
-  if (cfg.W1 <= 0 || cfg.mode == SV_MODE_SGBM_3WAY) return 0;
+  if (cfg.W1 <= 0 || cfg.mode == SV_MODE_SGBM_3WAY || cfg.D > kDPL * 16) return 0;
   return (int)(5ll * numSM / (2ll * groups_of(cfg, false, kK)));
 }
 static int num_sms() {
@@ -884,11 +884,11 @@ static int num_sms() {
 }
 size_t sgbm_s_frames(const SgbmCfg& cfg, int nframes) { return nframes <= split_limit(cfg, num_sms()) ? 2 * (size_t)nframes : (size_t)nframes; }
 size_t sgbm_flags_bytes(const SgbmCfg& cfg, int nframes) {
-  if (cfg.W1 <= 0) return 256;
+  if (cfg.W1 <= 0 || cfg.D > kDPL * 16) return 256;
   return 2 * flag_ints(cfg, nframes) * sizeof(int);
 }
 size_t sgbm_edges_bytes(const SgbmCfg& cfg, int nframes) {
-  if (cfg.W1 <= 0) return 256;
+  if (cfg.W1 <= 0 || cfg.D > kDPL * 16) return 256;
   return edge_u4(cfg, (int)sgbm_s_frames(cfg, nframes)) * sizeof(uint4);
 }
 
@@ -905,6 +905,10 @@ cudaError_t sgbm_aggregate_sweep(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   // a single small pair: one worker per line and direction instead of the strip pipeline (sgbm_lines.cu)
   if (!debugS && sgbm_lines_ok(cfg, nframes, sc.frameCells) && sc.sBytes >= sgbm_lines_frames(cfg, nframes) * sc.frameCells * 2)
     return sgbm_aggregate_lines(cfg, sc, nframes, st, stats);
+  if (cfg.D > kDPL * 16) {   // beyond 16 lanes per pixel only the line form exists (it walks the call pair by pair)
+    if (debugS || sc.sBytes < sgbm_lines_frames(cfg, 1) * sc.frameCells * 2) return cudaErrorNotSupported;
+    return sgbm_aggregate_lines(cfg, sc, nframes, st, stats);
+  }
   int dev = 0, numSM = 0;
   cudaError_t e0 = cudaGetDevice(&dev);
   if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev);

@@ -238,6 +238,44 @@ def save_sgbm3(path):
     print("wrote", path, os.path.getsize(path), "bytes", n, "cases")
 
 
+def save_sgbm_wide(path):
+    """cv2.StereoSGBM with more than 256 disparities (272 .. 512): gray pairs in the three modes, and 8UC3 / large-block cases."""
+    out = {}
+    n = 0
+    rng = np.random.default_rng(777)
+    keys = ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap", "uniquenessRatio", "speckleWindowSize",
+            "speckleRange", "mode")
+
+    def add(l, r, k):
+        nonlocal n
+        out[f"l{n}"], out[f"r{n}"], out[f"d{n}"] = l, r, cv_sgbm(l, r, k)
+        out[f"p{n}"] = np.array([k[x] for x in keys], np.int32)
+        n += 1
+
+    for (H, W, D, bs, minD) in [(26, 340, 272, 7, 0), (22, 470, 384, 5, 0), (24, 590, 512, 7, 0), (20, 420, 320, 3, -6), (18, 600, 512, 11, 3)]:
+        P1, P2 = 8 * bs * bs, 32 * bs * bs
+        l, r = synth_pair(H, W, D, seed=H)
+        for mode in (cv2.STEREO_SGBM_MODE_SGBM, cv2.STEREO_SGBM_MODE_HH, cv2.STEREO_SGBM_MODE_HH4):
+            add(l, r, dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=min(P2, 2500), disp12MaxDiff=1, preFilterCap=31,
+                           uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=mode))
+        ln, rn = rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+        add(ln, rn, dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=min(P2, 2500), disp12MaxDiff=2, preFilterCap=63,
+                         uniquenessRatio=5, speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_HH))
+    # 8UC3 and blockSize 13 beyond 256 disparities
+    H, W, D = 20, 400, 320
+    l1, r1 = synth_pair(H, W, D, seed=5)
+    l3 = np.stack([l1, np.roll(l1, 1, axis=0) // 2 + 30, 255 - l1], axis=2).astype(np.uint8)
+    r3 = np.stack([r1, np.roll(r1, 1, axis=0) // 2 + 30, 255 - r1], axis=2).astype(np.uint8)
+    for mode in (cv2.STEREO_SGBM_MODE_HH, cv2.STEREO_SGBM_MODE_HH4):
+        add(l3, r3, dict(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=31, uniquenessRatio=10,
+                         speckleWindowSize=0, speckleRange=0, mode=mode))
+    add(l1, r1, dict(minDisparity=0, numDisparities=D, blockSize=13, P1=300, P2=1200, disp12MaxDiff=1, preFilterCap=15, uniquenessRatio=10,
+                     speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_HH))
+    out["n"] = np.array(n)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes", n, "cases")
+
+
 def save_sgbm3way(path):
     """cv2.StereoSGBM MODE_SGBM_3WAY: textured and noise pairs (noise exercises the tie-breaking of OpenCV's vectorised
     winner search and its uniqueness threshold), images smaller than the stripe overlap, minDisparity of both signs."""
@@ -416,7 +454,7 @@ def save_calibration_yml(path):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    jobs = dict(big_sha=save_big, sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way)
+    jobs = dict(big_sha=save_big, sgbm_small=save_sgbm, bm_small=save_bm, stages_small=save_stages, bottle=save_bottle, rectify_small=save_rectify, bm_mind_small=save_bm_mind, sgbm3_small=save_sgbm3, sgbm3way_small=save_sgbm3way, sgbm_wide=save_sgbm_wide)
     for name, fn in jobs.items():
         if not only or name in only:
             fn(os.path.join(HERE, name + ".npz"))

@@ -23,6 +23,13 @@ def sgbm_golden_cases():
         yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]
 
 
+def sgbm_wide_cases():
+    """cv2 cases with 272 .. 512 disparities (gray, 8UC3, blockSize 11 / 13); tests/golden/make_golden.py: save_sgbm_wide"""
+    g = golden("sgbm_wide")
+    for i in range(int(g["n"])):
+        yield i, g[f"l{i}"], g[f"r{i}"], dict(zip(SGBM_KEYS, (int(v) for v in g[f"p{i}"]))), g[f"d{i}"]
+
+
 def bm_golden_cases():
     g = golden("bm_small")
     for i in range(int(g["n"])):

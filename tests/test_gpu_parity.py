@@ -7,7 +7,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import REF_PARAMS, bm_golden_cases, golden, nmismatch, sgbm_golden_cases
+from helpers import REF_PARAMS, bm_golden_cases, golden, nmismatch, sgbm_golden_cases, sgbm_wide_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,29 @@ def test_sgbm_golden_all_modes(svgpu):
         with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
             ctx.set_sgbm(**prm)
             assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
+
+
+def test_sgbm_wide_disparity_golden(svgpu, oracle):
+    """numDisparities 272 .. 512 (a full warp per pixel: only the line form of the aggregation serves them, pair by pair) against
+    cv2's outputs: gray in the three modes, 8UC3, blockSize 11 / 13; then a batch of three pairs == single calls."""
+    n = 0
+    for i, l, r, prm, want in sgbm_wide_cases():
+        H, W = l.shape[:2]
+        with svgpu.Context(W, H) as ctx:
+            ctx.set_sgbm(**prm)
+            assert nmismatch(ctx.sgbm(l, r), want) == 0, (i, prm)
+        n += 1
+    assert n >= 20
+    from svgpu.synth import synth_batch
+    H, W, D = 30, 600, 512
+    L, R = synth_batch(3, H, W, D, seed0=3)
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**prm)
+        got = ctx.sgbm_batch(L, R)
+        for k in range(3):
+            assert nmismatch(got[k], ctx.sgbm(L[k], R[k])) == 0
+        assert nmismatch(got[0], oracle.sgbm(L[0], R[0], **prm)) == 0
 
 
 def test_sgbm_three_channel_golden(svgpu, oracle):
@@ -93,7 +116,7 @@ def test_sgbm_too_narrow_matches_reference_error(svgpu):
 
 def test_invalid_settings_and_images(svgpu):
     with svgpu.Context(64, 48) as ctx:
-        for bad in (dict(numDisparities=24), dict(numDisparities=512), dict(numDisparities=32, mode=4), dict(numDisparities=32, mode=2, uniquenessRatio=100),
+        for bad in (dict(numDisparities=24), dict(numDisparities=528), dict(numDisparities=272, mode=2), dict(numDisparities=32, mode=4), dict(numDisparities=32, mode=2, uniquenessRatio=100),
                     dict(numDisparities=32, blockSize=4), dict(numDisparities=32, P2=30000)):
             prm = dict(REF_PARAMS, mode=1)
             prm.update(bad)
@@ -367,7 +390,7 @@ def test_sgbm_random_configs_bit_exact(svgpu, oracle, sweep_k, sweep_split, line
     rng = np.random.default_rng(20261018)
     bad = []
     for case in range(48):
-        D = int(rng.choice([16, 32, 48, 64, 80, 96, 128, 160, 224, 256]))
+        D = int(rng.choice([16, 32, 48, 64, 80, 96, 128, 160, 224, 256, 320, 512]))
         minD = int(rng.choice([0, 0, 0, 3, -5, 16, -16]))
         bs = int(rng.choice([1, 3, 5, 7, 9, 11]))
         mode = int(rng.choice([0, 1, 3]))

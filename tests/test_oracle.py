@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from helpers import (bm_golden_cases, bm_mind_golden_cases, golden, nmismatch, sgbm3_golden_cases, sgbm3way_golden_cases,
-                     sgbm_golden_cases)
+                     sgbm_golden_cases, sgbm_wide_cases)
 
 
 def test_sgbm_golden(oracle):
@@ -16,6 +16,15 @@ def test_sgbm_golden(oracle):
         assert nmismatch(got, want) == 0, (i, prm)
         n += 1
     assert n > 100
+
+
+def test_sgbm_wide_disparity_golden(oracle):
+    """numDisparities 272 .. 512 against cv2 (gray in the three modes, 8UC3, blockSize 11 / 13)."""
+    n = 0
+    for i, l, r, prm, want in sgbm_wide_cases():
+        assert nmismatch(oracle.sgbm(l, r, **prm), want) == 0, (i, prm)
+        n += 1
+    assert n >= 20
 
 
 def test_sgbm_three_channel_golden(oracle):
