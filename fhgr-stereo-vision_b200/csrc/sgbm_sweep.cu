@@ -770,7 +770,7 @@ cudaError_t launch_full(const SweepArgs& a, int grid, cudaStream_t st) {
 template <int LPP, int PATHS, bool SECOND, int K, bool WAY3 = false>
 cudaError_t launch_nw(const SweepArgs& a, int grid, cudaStream_t st) {
   // the specialisations without idle lanes are built for the common modes only
-  if constexpr (!WAY3 && PATHS != P_H) {
+  if constexpr (!WAY3) {
     if (a.nAct == LPP) {
       if constexpr (PATHS == 15) {
         if (a.smallSums) return launch_full<LPP, PATHS, SECOND, K, WAY3, true, true>(a, grid, st);
