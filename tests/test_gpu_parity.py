@@ -711,3 +711,21 @@ def test_sgbm_block_sizes_13_and_15(svgpu, oracle):
             ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=17, P1=8, P2=32, preFilterCap=15, mode=1))
         with pytest.raises(svgpu.SvgpuError):   # 15 x 15 x (2 x 33 + 63) + P2 leaves the 16-bit cost range
             ctx.set_sgbm(**dict(REF_PARAMS, numDisparities=32, blockSize=15, P2=4000, mode=1))
+
+
+def test_mixed_call_sizes_on_one_context(svgpu, oracle):
+    """One context, calls of 1, 3, 12, 2, 40 and again 1 pairs (640x360, 64 disparities, MODE_HH): the library moves between the
+    line form, the side-by-side passes and the fused passes and regrows its scratch on the way; every pair must equal the
+    oracle's result for it, whatever call it travelled in."""
+    from svgpu.synth import synth_batch
+    H, W, D = 360, 640, 64
+    L, R = synth_batch(4, H, W, D, seed0=21)
+    prm = dict(REF_PARAMS, numDisparities=D, mode=1)
+    want = [oracle.sgbm(L[i], R[i], **prm) for i in range(4)]
+    with svgpu.Context(W, H) as ctx:
+        ctx.set_sgbm(**prm)
+        for n in (1, 3, 12, 2, 40, 1):
+            idx = np.arange(n) % 4
+            got = ctx.sgbm_batch(np.ascontiguousarray(L[idx]), np.ascontiguousarray(R[idx]))
+            for k in range(n):
+                assert nmismatch(got[k], want[idx[k]]) == 0, (n, k)
