@@ -121,7 +121,9 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
   // + 256: the TMA staging of the cost kernel copies whole 16-byte units and may read one operand word past a row
   const size_t planeBytes = (size_t)batch * g.H * 2 * cn * g.Wp * sizeof(uint2) + 256;
   // S holds one volume per pair, two when the passes of a few pairs run side by side, one per path for single small pairs
-  const size_t sFrames = way3 ? (size_t)batch : std::max(sgbm_s_frames(gs, batch), sgbm_lines_frames(gs, std::min(batch, sgbm_lines_max_frames(gs, cells))));
+  // (MODE_SGBM_3WAY: the line form counts stripe frames, four per pair, of cells / 4 each)
+  const size_t sFrames = way3 ? std::max<size_t>(batch, (sgbm_lines_frames(gs, std::min(4 * batch, sgbm_lines_max_frames(gs, cells / 4))) + 3) / 4)
+                              : std::max(sgbm_s_frames(gs, batch), sgbm_lines_frames(gs, std::min(batch, sgbm_lines_max_frames(gs, cells))));
   const size_t need[svgpu_ctx::kScratchBufs] = {
       planeBytes, planeBytes, (size_t)batch * cells * 2, sFrames * cells * 2, (size_t)batch * vrows * w1 * 8,
       (size_t)batch * (vrows + (way3 ? g.H : 0)) * g.W * 2, 256, sgbm_flags_bytes(gs, sweepFrames), sgbm_edges_bytes(gs, sweepFrames)};
@@ -158,9 +160,8 @@ int ensure_scratch(svgpu_ctx* c, int batch, int cn = 1) {
 int normalise_sgbm(svgpu_ctx* c, const svgpu_sgbm_params& p, SgbmCfg& g) {
   if (p.numDisparities <= 0 || p.numDisparities % 16 != 0) return fail(c, SV_INVALID_SETTINGS, "numDisparities must be a positive multiple of 16");
   // up to 256 disparities every form of the aggregation is built; up to 512 the line form (a full warp per pixel) serves all
-  // call sizes.  MODE_SGBM_3WAY has its own driver around the strip pipeline and stays within 256.
+  // call sizes
   if (p.numDisparities > 512) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 512 is not supported");
-  if (p.numDisparities > 256 && p.mode == SV_MODE_SGBM_3WAY) return fail(c, SV_INVALID_SETTINGS, "numDisparities > 256 is not supported in MODE_SGBM_3WAY");
   if (p.mode != SV_MODE_SGBM && p.mode != SV_MODE_HH && p.mode != SV_MODE_HH4 && p.mode != SV_MODE_SGBM_3WAY)
     return fail(c, SV_INVALID_SETTINGS, "mode must be MODE_SGBM, MODE_HH, MODE_SGBM_3WAY or MODE_HH4");
   // 15 x 15 is the largest block whose cost fits 16 bits at all (225 x 93 + P2, checked below)

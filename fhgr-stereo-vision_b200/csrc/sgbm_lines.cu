@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 2) k_lines(const LineArgs a) {
 }
 
 // S = saturating sum of the directions' volumes, then the winner-take-all of A.6: one pixel per worker
-template <int LPP>
+template <int LPP, bool WAY3>
 __global__ void __launch_bounds__(256) k_wta_lines(const LineArgs a) {
   constexpr int RW = 32 / LPP, NV = kNR / 4, VEC = LPP * NV;
   __shared__ uint4 sW[8 * RW * VEC];
@@ -169,13 +169,13 @@ __global__ void __launch_bounds__(256) k_wta_lines(const LineArgs a) {
       }
     }
     uint2 o;
-    sweep_wta<LPP, false>(s, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
+    sweep_wta<LPP, WAY3>(s, wta, gl, active, lane, a.D, a.uniqF, a.uniqMagic, o);
     if (on && gl == 0) a.sel[p] = o;
   }
 }
 
 template <int LPP>
-cudaError_t launch_lines(const LineArgs& a, int numSM, cudaStream_t st) {
+cudaError_t launch_lines(const LineArgs& a, bool way3, int numSM, cudaStream_t st) {
   constexpr int RW = 32 / LPP;
   const long long workers = (long long)a.nframes * a.lineBase[a.ndirs];
   const long long blocks = (workers + 8 * RW - 1) / (8 * RW);
@@ -184,11 +184,12 @@ cudaError_t launch_lines(const LineArgs& a, int numSM, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   const long long npix = (long long)a.H * a.W1 * a.nframes;
   const int grid = (int)std::min<long long>((npix + 8 * RW - 1) / (8 * RW), (long long)numSM * 32);
-  k_wta_lines<LPP><<<grid, 256, 0, st>>>(a);
+  if (way3) k_wta_lines<LPP, true><<<grid, 256, 0, st>>>(a);   // MODE_SGBM_3WAY has its own selection rule (sgbm_device.cuh)
+  else k_wta_lines<LPP, false><<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
-int ndirs_of(int mode) { return mode == SV_MODE_HH ? 8 : mode == SV_MODE_HH4 ? 4 : 5; }
+int ndirs_of(int mode) { return mode == SV_MODE_HH ? 8 : mode == SV_MODE_HH4 ? 4 : mode == SV_MODE_SGBM_3WAY ? 3 : 5; }
 
 }  // namespace
 
@@ -199,7 +200,8 @@ int ndirs_of(int mode) { return mode == SV_MODE_HH ? 8 : mode == SV_MODE_HH4 ? 4
 // 720p / 64 MODE_SGBM: 0.5 instead of 3.1 ms (1), 2.4 instead of 3.9 (8), 3.4 instead of 4.1 (12).
 // SVGPU_SWEEP_LINES=0|1 pins the choice (tests).
 int sgbm_lines_max_frames(const SgbmCfg& cfg, size_t frameCells) {
-  if (cfg.W1 <= 0 || cfg.mode == SV_MODE_SGBM_3WAY || frameCells == 0) return 0;
+  // (MODE_SGBM_3WAY: the frames are the four stripe frames of a pair, cfg.H their row count)
+  if (cfg.W1 <= 0 || frameCells == 0) return 0;
   if (cfg.D > 256) return 1;   // the only form built for more than 16 lanes per pixel: a call is served pair by pair
   const double perFrame = (double)frameCells * 2.0 * 3.0 * ndirs_of(cfg.mode);   // bytes moved per pair
   const char* f = std::getenv("SVGPU_SWEEP_LINES");
@@ -234,7 +236,8 @@ cudaError_t sgbm_aggregate_lines(const SgbmCfg& cfg, const SgbmScratch& sc, int 
   static const int hh[8][2] = {{1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {-1, -1}, {1, -1}, {0, 1}, {0, -1}};
   static const int hh4[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
   static const int sgbm5[5][2] = {{1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {0, 1}};
-  const int (*dirs)[2] = cfg.mode == SV_MODE_HH ? hh : cfg.mode == SV_MODE_HH4 ? hh4 : sgbm5;
+  static const int way3[3][2] = {{1, 0}, {-1, 0}, {0, 1}};
+  const int (*dirs)[2] = cfg.mode == SV_MODE_HH ? hh : cfg.mode == SV_MODE_HH4 ? hh4 : cfg.mode == SV_MODE_SGBM_3WAY ? way3 : sgbm5;
   a.ndirs = ndirs_of(cfg.mode);
   a.lineBase[0] = 0;
   for (int k = 0; k < a.ndirs; k++) {
@@ -253,12 +256,12 @@ cudaError_t sgbm_aggregate_lines(const SgbmCfg& cfg, const SgbmScratch& sc, int 
     a.C = (const uint4*)sc.C + (size_t)f0 * a.frameU4;
     a.sel = (uint2*)sc.sel + (size_t)f0 * cfg.H * cfg.W1;
     switch (lpp) {
-      case 1: e = launch_lines<1>(a, numSM, st); break;
-      case 2: e = launch_lines<2>(a, numSM, st); break;
-      case 4: e = launch_lines<4>(a, numSM, st); break;
-      case 8: e = launch_lines<8>(a, numSM, st); break;
-      case 16: e = launch_lines<16>(a, numSM, st); break;
-      default: e = launch_lines<32>(a, numSM, st); break;
+      case 1: e = launch_lines<1>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
+      case 2: e = launch_lines<2>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
+      case 4: e = launch_lines<4>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
+      case 8: e = launch_lines<8>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
+      case 16: e = launch_lines<16>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
+      default: e = launch_lines<32>(a, cfg.mode == SV_MODE_SGBM_3WAY, numSM, st); break;
     }
     if (stats) stats->launches += 2;
   }

@@ -61,7 +61,7 @@ enum { SV_MODE_SGBM = 0, SV_MODE_HH = 1, SV_MODE_SGBM_3WAY = 2, SV_MODE_HH4 = 3 
  * Values are normalised the way OpenCV does (P1<=0 -> 2, uniquenessRatio<0 -> 10, ...). */
 typedef struct svgpu_sgbm_params {
   int minDisparity;      /* :250 */
-  int numDisparities;    /* :251, multiple of 16, <= 512 (<= 256 in MODE_SGBM_3WAY) */
+  int numDisparities;    /* :251, multiple of 16, <= 512 */
   int blockSize;         /* :249, odd, 1..15 (as far as blockSize^2 * (2 * ftzero + 63) + P2 fits 16 bits, OpenCV's own cost type) */
   int P1;                /* :257 */
   int P2;                /* :258 */

@@ -271,6 +271,11 @@ def save_sgbm_wide(path):
                          speckleWindowSize=0, speckleRange=0, mode=mode))
     add(l1, r1, dict(minDisparity=0, numDisparities=D, blockSize=13, P1=300, P2=1200, disp12MaxDiff=1, preFilterCap=15, uniquenessRatio=10,
                      speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_HH))
+    # MODE_SGBM_3WAY beyond 256 disparities (four stripe frames per pair)
+    for (H, W, D) in [(37, 340, 272), (26, 590, 512)]:
+        l, r = synth_pair(H, W, D, seed=H + 1)
+        add(l, r, dict(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=31, uniquenessRatio=10,
+                       speckleWindowSize=0, speckleRange=0, mode=cv2.STEREO_SGBM_MODE_SGBM_3WAY))
     out["n"] = np.array(n)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes", n, "cases")

@@ -79,11 +79,14 @@ def test_sgbm_three_channel_golden(svgpu, oracle):
         assert e.value.code == svgpu._abi.SV_INVALID_SETTINGS
 
 
-def test_sgbm_3way_golden(svgpu, oracle):
+@pytest.mark.parametrize("lines", ["0", "1"])
+def test_sgbm_3way_golden(svgpu, oracle, lines, monkeypatch):
     """MODE_SGBM_3WAY (four stripe frames per pair, forward H+V sweep, backward H sweep, OpenCV's vectorised selection rule):
     bit-exact against cv2's output incl. noise pairs (ties) and images smaller than the stripe overlap; batch == single; an
-    8UC3 pair against the oracle; uniquenessRatio = 100 is refused (cv2 dies with SIGFPE there)."""
+    8UC3 pair against the oracle; uniquenessRatio = 100 is refused (cv2 dies with SIGFPE there).  Once through the strip
+    pipeline and once through the line form (three directions per stripe frame, the same selection rule)."""
     from helpers import sgbm3way_golden_cases
+    monkeypatch.setenv("SVGPU_SWEEP_LINES", lines)
     for i, l, r, prm, want in sgbm3way_golden_cases():
         with svgpu.Context(l.shape[1], l.shape[0]) as ctx:
             ctx.set_sgbm(**prm)
@@ -116,7 +119,7 @@ def test_sgbm_too_narrow_matches_reference_error(svgpu):
 
 def test_invalid_settings_and_images(svgpu):
     with svgpu.Context(64, 48) as ctx:
-        for bad in (dict(numDisparities=24), dict(numDisparities=528), dict(numDisparities=272, mode=2), dict(numDisparities=32, mode=4), dict(numDisparities=32, mode=2, uniquenessRatio=100),
+        for bad in (dict(numDisparities=24), dict(numDisparities=528), dict(numDisparities=32, mode=4), dict(numDisparities=32, mode=2, uniquenessRatio=100),
                     dict(numDisparities=32, blockSize=4), dict(numDisparities=32, P2=30000)):
             prm = dict(REF_PARAMS, mode=1)
             prm.update(bad)
