@@ -732,3 +732,22 @@ def test_mixed_call_sizes_on_one_context(svgpu, oracle):
             got = ctx.sgbm_batch(np.ascontiguousarray(L[idx]), np.ascontiguousarray(R[idx]))
             for k in range(n):
                 assert nmismatch(got[k], want[idx[k]]) == 0, (n, k)
+
+
+def test_sgbm_mode_block_disparity_combinations(svgpu, oracle):
+    """Corners of the contract together: blockSize 13 / 15 with MODE_SGBM_3WAY and with 272 .. 512 disparities, 512 disparities
+    in MODE_SGBM_3WAY and MODE_HH4 — on a textured and on a noise pair each, against the oracle."""
+    from svgpu.synth import synth_pair
+    rng = np.random.default_rng(1)
+    for (H, W, D, bs, mode, cap, P1, P2) in [(40, 200, 64, 13, 2, 15, 300, 1200), (38, 420, 320, 15, 2, 15, 100, 400), (30, 600, 512, 15, 3, 15, 100, 400),
+                                             (33, 380, 272, 13, 0, 15, 300, 1200), (44, 300, 128, 15, 1, 15, 100, 300), (36, 560, 512, 9, 2, 31, 200, 800)]:
+        for kind in ("synth", "noise"):
+            if kind == "synth":
+                l, r = synth_pair(H, W, D, seed=H)
+            else:
+                l, r = rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+            prm = dict(minDisparity=0, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=1, preFilterCap=cap, uniquenessRatio=10,
+                       speckleWindowSize=0, speckleRange=0, mode=mode)
+            with svgpu.Context(W, H) as ctx:
+                ctx.set_sgbm(**prm)
+                assert nmismatch(ctx.sgbm(l, r), oracle.sgbm(l, r, **prm)) == 0, (H, W, D, bs, mode, kind)
