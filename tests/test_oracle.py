@@ -155,3 +155,20 @@ def test_live_cv2_large_blocks(oracle, cv2):
                    uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=mode)
         assert bs * bs * (2 * 15 + 63) + 400 <= 32767
         assert nmismatch(oracle.sgbm(l, r, **prm), cv2.StereoSGBM_create(**prm).compute(l, r)) == 0, prm
+
+
+def test_live_cv2_contract_corners(oracle, cv2):
+    """blockSize 13 / 15 together with MODE_SGBM_3WAY and with 272 .. 512 disparities (the combinations the GPU test
+    test_sgbm_mode_block_disparity_combinations compares with the oracle): oracle == cv2."""
+    from svgpu.synth import synth_pair
+    rng = np.random.default_rng(1)
+    for (H, W, D, bs, mode, cap, P1, P2) in [(40, 200, 64, 13, 2, 15, 300, 1200), (38, 420, 320, 15, 2, 15, 100, 400), (30, 600, 512, 15, 3, 15, 100, 400),
+                                             (33, 380, 272, 13, 0, 15, 300, 1200), (44, 300, 128, 15, 1, 15, 100, 300), (36, 560, 512, 9, 2, 31, 200, 800)]:
+        for kind in ("synth", "noise"):
+            if kind == "synth":
+                l, r = synth_pair(H, W, D, seed=H)
+            else:
+                l, r = rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+            prm = dict(minDisparity=0, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=1, preFilterCap=cap, uniquenessRatio=10,
+                       speckleWindowSize=0, speckleRange=0, mode=mode)
+            assert nmismatch(oracle.sgbm(l, r, **prm), cv2.StereoSGBM_create(**prm).compute(l, r)) == 0, prm
