@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256, 2) k_lines(const LineArgs a) {
   const long long total = (long long)a.nframes * linesPerFrame;
   const long long gw = ((long long)blockIdx.x * 8 + warp) * RW + j;
   const bool valid = gw < total;
-  int len = 0, dOff = 0;
+  int len = 0;
+  unsigned dOff = 0;   // step between the pixels of the line in uint4, modulo 2^32 (negative steps wrap)
   unsigned off = 0;
   const uint4* Cp = a.C;
   uint4* Lp = a.L;
@@ -94,22 +95,22 @@ __global__ void __launch_bounds__(256, 2) k_lines(const LineArgs a) {
       len = min(W1, dy > 0 ? H - y0 : y0 + 1);
     }
     off = ((unsigned)y0 * (unsigned)W1 + (unsigned)x0) * (unsigned)a.pixU4 + (unsigned)((active ? gl : 0) * NV);
-    dOff = (dy * W1 + dx) * a.pixU4;
+    dOff = (unsigned)((dy * W1 + dx) * a.pixU4);
     Cp = a.C + (size_t)frame * a.frameU4;
     Lp = a.L + (size_t)k * a.dirU4 + (size_t)frame * a.frameU4;
   }
   const int maxLen = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)len);   // the workers of a warp walk in lock step
 
-  // offsets are formed modulo 2^32 before they meet a pointer: dOff may be negative
+  // offsets are formed modulo 2^32 (unsigned arithmetic) before they meet a pointer: a volume has fewer than 2^32 uint4
   uint4 cb[kPF][NV];
 #pragma unroll
   for (int q = 0; q < kPF; q++) {
-    const unsigned o = q < len ? off + (unsigned)(q * dOff) : 0u;
+    const unsigned o = q < len ? off + (unsigned)q * dOff : 0u;
 #pragma unroll
     for (int h = 0; h < NV; h++) cb[q][h] = __ldg(Cp + o + h);
   }
   for (int q = kPF; q < kL2Ahead; q++)
-    if (q < len) prefetch_l2(Cp + (off + (unsigned)(q * dOff)));
+    if (q < len) prefetch_l2(Cp + (off + (unsigned)q * dOff));
   uint32_t L[kNR];
 #pragma unroll
   for (int q = 0; q < kNR; q++) L[q] = 0;
@@ -123,15 +124,15 @@ __global__ void __launch_bounds__(256, 2) k_lines(const LineArgs a) {
       for (int h = 0; h < NV; h++) { c[4 * h] = cb[q][h].x; c[4 * h + 1] = cb[q][h].y; c[4 * h + 2] = cb[q][h].z; c[4 * h + 3] = cb[q][h].w; }
       {
         // always load (from a safe address past the end of the line) so that the data lands in the ring registers directly
-        const unsigned o = t + kPF < len ? off + (unsigned)((t + kPF) * dOff) : 0u;
+        const unsigned o = t + kPF < len ? off + (unsigned)(t + kPF) * dOff : 0u;
 #pragma unroll
         for (int h = 0; h < NV; h++) cb[q][h] = __ldg(Cp + o + h);
-        if (t + kL2Ahead < len) prefetch_l2(Cp + (off + (unsigned)((t + kL2Ahead) * dOff)));   // this lane's 32 bytes of that pixel
+        if (t + kL2Ahead < len) prefetch_l2(Cp + (off + (unsigned)(t + kL2Ahead) * dOff));   // this lane's 32 bytes of that pixel
       }
       const uint32_t lm = sweep_path_core<LPP>(L, m, t == 0, c, kc, gl, lastLane, active, lane);
       m = group_min_u32<LPP>(lm, lane);
       if (t < len && active) {
-        uint4* dst = Lp + (off + (unsigned)(t * dOff));
+        uint4* dst = Lp + (off + (unsigned)t * dOff);
 #pragma unroll
         for (int h = 0; h < NV; h++) dst[h] = make_uint4(L[4 * h], L[4 * h + 1], L[4 * h + 2], L[4 * h + 3]);
       }
